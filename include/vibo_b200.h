@@ -1,0 +1,171 @@
+/*
+ * vibo_b200.h -- C ABI of the B200-native VIBO ELBO engine (libvibo_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of mhw32/variational-item-response-theory:
+ * the amortized ELBO forward/backward of src/torch_core/models.py
+ * (VIBO_{1,2,3}PL.forward :337-354, .encode :356-371, .decode :373-378,
+ * .elbo :380-443) together with the helpers of src/utils.py (:46-49, :59-67,
+ * :85-88, :105-113) it calls.  The reference has no FFI of its own (100 %
+ * Python on stock PyTorch ops); these entry points are what a ctypes binding
+ * for that path binds -- see INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - Every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter name ends in _host.  All buffers are caller-owned and
+ *     contiguous row-major; the library allocates nothing persistent.
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises except the *_host ones, which say so.
+ *   - Return value: 0 on success, a negative vibo_status otherwise; the
+ *     message for the calling thread's last failure is vibo_last_error().
+ *   - P persons (rows), I items (columns), D ability dims, F item-feature
+ *     width: 1 (1PL), D+1 (2PL), D+2 (3PL)   [models.py:331, :523, :538].
+ *   - response: float32 (P, I), values 0/1; missing cells hold anything
+ *     (-1 by convention, src/config.py:14).   mask: uint8/bool (P, I),
+ *     non-zero = observed  [src/datasets.py:928-940 emits exactly these].
+ *   - table: float32 (2, It, 2D): raw encoder outputs (mean | log-variance)
+ *     of AbilityInferenceNetwork.mlp (models.py:575-582, :599) for response
+ *     value r = 0, 1; It = 1 for the unconditional encoder, It = I for
+ *     ConditionalAbilityInferenceNetwork (models.py:695-710).
+ */
+#ifndef VIBO_B200_H_
+#define VIBO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIBO_B200_VERSION 100 /* 0.1.0 */
+#define VIBO_MAX_ABILITY_DIM 8
+
+typedef enum {
+  VIBO_OK = 0,
+  VIBO_ERR_BAD_ARGUMENT = -1, /* null pointer, negative size, bad enum      */
+  VIBO_ERR_UNSUPPORTED = -2,  /* D > VIBO_MAX_ABILITY_DIM, I too large ...  */
+  VIBO_ERR_MISALIGNED = -3,   /* pointer not aligned as documented          */
+  VIBO_ERR_WORKSPACE = -4,    /* workspace too small                        */
+  VIBO_ERR_CUDA = -5          /* a CUDA runtime call failed                 */
+} vibo_status;
+
+/* replace_missing_with_prior (models.py:614-618) vs --drop-missing */
+#define VIBO_MISSING_PRIOR 0
+#define VIBO_MISSING_DROP 1
+/* elbo(): use_kl_divergence=True (models.py:427-430) vs False (:432-441) */
+#define VIBO_ELBO_KL 0
+#define VIBO_ELBO_SAMPLE 1
+
+typedef struct {
+  int64_t num_person;     /* P: rows held by this call (one shard)            */
+  int32_t num_item;       /* I                                                */
+  int32_t ability_dim;    /* D, 1..VIBO_MAX_ABILITY_DIM                       */
+  int32_t irt_model;      /* 1, 2, 3  (VIBO_1PL / 2PL / 3PL)                  */
+  int32_t conditional;    /* 0: table is (2,1,2D); 1: table is (2,I,2D)       */
+  int32_t missing_policy; /* VIBO_MISSING_*                                   */
+  int32_t elbo_form;      /* VIBO_ELBO_*                                      */
+  int64_t person_offset;  /* global index of row 0 (keys the in-kernel Philox) */
+} vibo_desc;
+
+int vibo_version(void);
+const char* vibo_last_error(void);
+
+/* Bytes of scratch the calls below need for `desc` (an upper bound valid for
+ * every entry point).  The scratch holds per-CTA partial sums; it need not be
+ * zeroed. */
+size_t vibo_workspace_bytes(const vibo_desc* desc);
+
+/*
+ * Fused ELBO: replaces, in ONE pass over the response matrix,
+ *   encode   models.py:364-368   (PoE ability posterior + reparameterised draw)
+ *   decode   models.py:373, :729-766 (IRT link)
+ *   elbo     models.py:399 (masked Bernoulli LL, utils.py:46-49) and the
+ *            per-person prior term :428 (KL, utils.py:85-88) or :433-435.
+ * response_mu is never materialised.
+ *
+ *   eps_ability  (P, D) standard-normal draws (models.py:509), or NULL to
+ *                draw them in-kernel with Philox4x32-10 keyed by
+ *                (seed, person_offset + row).
+ *   out_scalars  double[2]: { LL = sum_ij o_ij ll_ij ,  person_term } where
+ *                person_term = KL(q(theta)||N(0,1)) summed over persons
+ *                (VIBO_ELBO_KL) or sum_i log p(theta_i) - log q(theta_i)
+ *                (VIBO_ELBO_SAMPLE).
+ *   ability_mu, ability_logvar, ability   (P, D) each, or NULL to skip.
+ *   g_table (2, It, 2D), g_item (I, F): gradients of
+ *                loss_k = -LL + beta * KL                 (VIBO_ELBO_KL)
+ *                loss_k = -LL - person_term               (VIBO_ELBO_SAMPLE)
+ *                w.r.t. table and item_feat (link path only); both NULL for a
+ *                forward-only evaluation.  Overwritten, not accumulated.
+ */
+int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                    const float* table, const float* item_feat, const float* eps_ability,
+                    uint64_t seed, float beta, double* out_scalars, float* ability_mu,
+                    float* ability_logvar, float* ability, float* g_table, float* g_item,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Same computation with response / mask in HOST memory (pinned or pageable):
+ * rows are streamed host->device in person chunks on an internal copy stream,
+ * overlapped with the kernel on the previous chunk; results (out_scalars and
+ * the gradient buffers) are DEVICE buffers as above and `out_scalars_host`
+ * (double[2], may be NULL) receives a copy.  Synchronises `stream` before
+ * returning.  staging: device scratch of vibo_host_staging_bytes() bytes.
+ */
+size_t vibo_host_staging_bytes(const vibo_desc* desc, int64_t chunk_person);
+int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
+                         const uint8_t* mask_host, const float* table, const float* item_feat,
+                         const float* eps_ability, uint64_t seed, float beta,
+                         double* out_scalars, double* out_scalars_host, float* g_table,
+                         float* g_item, int64_t chunk_person, void* staging,
+                         size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/*
+ * encode: product-of-experts ability posterior only.
+ * Replaces AbilityInferenceNetwork._forward_product (models.py:596-629) +
+ * product_of_experts (utils.py:105-113).  precision_sum (P, D) = sum of expert
+ * precisions (saved for the backward).
+ */
+int vibo_encode(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                const float* table, float* ability_mu, float* ability_logvar,
+                float* precision_sum, void* stream);
+
+/*
+ * Backward of vibo_encode: given d loss / d ability_mu and d loss /
+ * d ability_logvar (P, D), writes d loss / d table (2, It, 2D).
+ */
+int vibo_encode_backward(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                         const float* table, const float* ability_mu,
+                         const float* precision_sum, const float* g_ability_mu,
+                         const float* g_ability_logvar, float* g_table, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/*
+ * link + log-likelihood without materialising response_mu:
+ *   LL = sum_ij o_ij log Bernoulli(x_ij ; irt_model(ability, item_feat))
+ * (models.py:729-766 + utils.py:46-49 + the .sum() of models.py:399).
+ * out_ll: double[1].  g_ability (P, D), g_item (I, F): d LL / d ability and
+ * d LL / d item_feat, or both NULL.
+ */
+int vibo_link_loglik(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                     const float* ability, const float* item_feat, double* out_ll,
+                     float* g_ability, float* g_item, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* decode: response_mu (P, I) = irt_model_{1,2,3}pl(ability, item_feat),
+ * models.py:729-766 (API-parity path; the fused entry never needs it). */
+int vibo_decode(const vibo_desc* desc, const float* ability, const float* item_feat,
+                float* response_mu, void* stream);
+
+/* masked_bernoulli_log_pdf(...).sum() on a materialised response_mu
+ * (utils.py:46-49, models.py:399).  out_ll: double[1];  g_prob (P, I) =
+ * d LL / d response_mu or NULL. */
+int vibo_bernoulli_loglik(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                          const float* response_mu, double* out_ll, float* g_prob,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIBO_B200_H_ */

@@ -1,0 +1,83 @@
+"""ctypes binding of libvibo_b200.so (C ABI declared in include/vibo_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc,
+sm_100a).  There is no fallback: if the library is missing or a symbol is
+absent, importing/using the kernels raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvibo_b200.so")
+
+MISSING_PRIOR, MISSING_DROP = 0, 1
+ELBO_KL, ELBO_SAMPLE = 0, 1
+MAX_ABILITY_DIM = 8
+
+
+class Desc(C.Structure):
+    """``vibo_desc`` of include/vibo_b200.h."""
+    _fields_ = [
+        ("num_person", C.c_int64),
+        ("num_item", C.c_int32),
+        ("ability_dim", C.c_int32),
+        ("irt_model", C.c_int32),
+        ("conditional", C.c_int32),
+        ("missing_policy", C.c_int32),
+        ("elbo_form", C.c_int32),
+        ("person_offset", C.c_int64),
+    ]
+
+
+_p = C.c_void_p
+_PD = C.POINTER(Desc)
+
+# name -> (restype, argtypes); must list every symbol include/vibo_b200.h declares
+SIGNATURES = {
+    "vibo_version": (C.c_int, []),
+    "vibo_last_error": (C.c_char_p, []),
+    "vibo_workspace_bytes": (C.c_size_t, [_PD]),
+    "vibo_fused_elbo": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_uint64, C.c_float, _p, _p, _p, _p, _p,
+                                  _p, _p, C.c_size_t, _p]),
+    "vibo_host_staging_bytes": (C.c_size_t, [_PD, C.c_int64]),
+    "vibo_fused_elbo_host": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_uint64, C.c_float, _p, _p, _p, _p,
+                                       C.c_int64, _p, C.c_size_t, _p, C.c_size_t, _p]),
+    "vibo_encode": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p]),
+    "vibo_encode_backward": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "vibo_link_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "vibo_decode": (C.c_int, [_PD, _p, _p, _p, _p]),
+    "vibo_bernoulli_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise loudly if it (or any symbol) is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+            "There is no CPU or PyTorch fallback for the VIBO kernels.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class ViboError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().vibo_last_error()
+        raise ViboError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,279 @@
+// C ABI of libvibo_b200.so (see include/vibo_b200.h for the contract).
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "vibo_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  return fail(VIBO_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define VIBO_CUDA(call, where)                         \
+  do {                                                 \
+    cudaError_t e__ = (call);                          \
+    if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_desc(const vibo_desc* d) {
+  if (d == nullptr) return fail(VIBO_ERR_BAD_ARGUMENT, "desc is NULL");
+  if (d->num_person < 0 || d->num_item <= 0)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "num_person must be >= 0 and num_item > 0");
+  if (d->irt_model < 1 || d->irt_model > 3)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "irt_model must be 1, 2 or 3");
+  if (d->ability_dim < 1) return fail(VIBO_ERR_BAD_ARGUMENT, "ability_dim must be >= 1");
+  if (d->ability_dim > VIBO_MAX_ABILITY_DIM)
+    return fail(VIBO_ERR_UNSUPPORTED, "ability_dim > VIBO_MAX_ABILITY_DIM (8)");
+  if (d->missing_policy != VIBO_MISSING_PRIOR && d->missing_policy != VIBO_MISSING_DROP)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "missing_policy must be VIBO_MISSING_PRIOR or VIBO_MISSING_DROP");
+  if (d->elbo_form != VIBO_ELBO_KL && d->elbo_form != VIBO_ELBO_SAMPLE)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "elbo_form must be VIBO_ELBO_KL or VIBO_ELBO_SAMPLE");
+  if (d->conditional != 0 && d->conditional != 1)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "conditional must be 0 or 1");
+  return VIBO_OK;
+}
+
+int check_items(const vibo_desc* d) {
+  if (d->num_item > vibo::general_max_items(d->ability_dim)) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "num_item %d exceeds the limit %d for ability_dim %d", d->num_item,
+             vibo::general_max_items(d->ability_dim), d->ability_dim);
+    return fail(VIBO_ERR_UNSUPPORTED, buf);
+  }
+  return VIBO_OK;
+}
+
+// Carves the workspace of the composed (multi-pass) path.
+struct Carve {
+  char* base;
+  size_t off = 0, cap;
+  Carve(void* p, size_t n) : base(static_cast<char*>(p)), cap(n) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+size_t general_workspace_bytes(const vibo_desc* d) {
+  const size_t P = (size_t)d->num_person, I = (size_t)d->num_item, D = (size_t)d->ability_dim;
+  const size_t F = (size_t)vibo::item_width_host(d->irt_model, d->ability_dim);
+  const size_t G = (size_t)vibo::sm_count() * 8;  // upper bound of general_grid / person_grid
+  size_t b = 0;
+  b += align_up(8 * (G + 8), 256) * 3;                      // double partials
+  b += (align_up(4 * P * D, 256) + 256) * 8;                // per-person float scratch
+  b += align_up(4 * G * I * F, 256) + 256;                  // item-gradient partials
+  b += align_up(4 * G * 2 * I * 2 * D, 256) + 256;          // expert-table partials
+  return b + 4096;
+}
+
+}  // namespace
+
+namespace vibo {
+int item_width_host(int model, int D) { return model == 1 ? 1 : (model == 2 ? D + 1 : D + 2); }
+}  // namespace vibo
+
+extern "C" {
+
+int vibo_version(void) { return VIBO_B200_VERSION; }
+
+const char* vibo_last_error(void) { return g_last_error.c_str(); }
+
+size_t vibo_workspace_bytes(const vibo_desc* desc) {
+  if (check_desc(desc) != VIBO_OK) return 0;
+  const size_t a = general_workspace_bytes(desc);
+  const size_t b = vibo::fused_workspace_bytes(*desc);
+  return a > b ? a : b;
+}
+
+int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                    const float* table, const float* item_feat, const float* eps_ability,
+                    uint64_t seed, float beta, double* out_scalars, float* ability_mu,
+                    float* ability_logvar, float* ability, float* g_table, float* g_item,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!response || !mask || !table || !item_feat || !out_scalars)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "response, mask, table, item_feat and out_scalars are required");
+  if ((g_table == nullptr) != (g_item == nullptr))
+    return fail(VIBO_ERR_BAD_ARGUMENT, "g_table and g_item must both be given or both be NULL");
+  if (workspace == nullptr || workspace_bytes < vibo_workspace_bytes(desc))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_workspace_bytes(desc)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const vibo_desc& d = *desc;
+  if (d.num_person == 0) {
+    VIBO_CUDA(cudaMemsetAsync(out_scalars, 0, 2 * sizeof(double), st), "memset");
+    const int F = vibo::item_width_host(d.irt_model, d.ability_dim);
+    if (g_item) {
+      VIBO_CUDA(cudaMemsetAsync(g_item, 0, sizeof(float) * d.num_item * F, st), "memset");
+      VIBO_CUDA(cudaMemsetAsync(g_table, 0,
+                                sizeof(float) * 2 * (d.conditional ? d.num_item : 1) * 2 * d.ability_dim, st),
+                "memset");
+    }
+    return VIBO_OK;
+  }
+  if (vibo::fused_supported(d, response, mask)) {
+    VIBO_CUDA(vibo::launch_fused(d, response, mask, table, item_feat, eps_ability, seed, beta,
+                                 out_scalars, ability_mu, ability_logvar, ability, g_table, g_item,
+                                 workspace, workspace_bytes, false, st),
+              "fused kernel");
+    return VIBO_OK;
+  }
+  if (int rc = check_items(desc)) return rc;
+
+  // Composition of the general kernels (three passes over the rows).
+  const bool grad = g_item != nullptr;
+  const size_t PD = (size_t)d.num_person * d.ability_dim;
+  const size_t F = (size_t)vibo::item_width_host(d.irt_model, d.ability_dim);
+  const size_t G = (size_t)vibo::sm_count() * 8;
+  Carve ws(workspace, workspace_bytes);
+  double* part_ll = ws.take<double>(G + 8);
+  double* part_term = ws.take<double>(G + 8);
+  float* S = ws.take<float>(PD);
+  float* amu = ability_mu ? ability_mu : ws.take<float>(PD);
+  float* alv = ability_logvar ? ability_logvar : ws.take<float>(PD);
+  float* th = ability ? ability : ws.take<float>(PD);
+  float* eps_buf = ws.take<float>(PD);
+  float* g_ab = ws.take<float>(PD);
+  float* g_mu = ws.take<float>(PD);
+  float* g_lv = ws.take<float>(PD);
+  float* part_g = ws.take<float>(G * d.num_item * F);
+  float* part_ab = ws.take<float>(G * 2 * d.num_item * 2 * d.ability_dim);
+  if (!ws.ok()) return fail(VIBO_ERR_WORKSPACE, "workspace carve overflow");
+
+  VIBO_CUDA(vibo::launch_encode(d, response, mask, table, amu, alv, S, st), "encode");
+  VIBO_CUDA(vibo::launch_person_forward(d, amu, alv, eps_ability, seed,
+                                        eps_ability ? nullptr : eps_buf, th, part_term,
+                                        out_scalars + 1, st),
+            "person_forward");
+  VIBO_CUDA(vibo::launch_link(d, response, mask, th, item_feat, out_scalars, grad ? g_ab : nullptr,
+                              g_item, part_ll, part_g, st),
+            "link");
+  if (grad) {
+    VIBO_CUDA(vibo::launch_negate(g_item, (int)(d.num_item * F), st), "negate");
+    VIBO_CUDA(vibo::launch_person_backward(d, beta, amu, alv, eps_ability ? eps_ability : eps_buf, th,
+                                           g_ab, g_mu, g_lv, st),
+              "person_backward");
+    VIBO_CUDA(vibo::launch_encode_bwd(d, response, mask, table, amu, S, g_mu, g_lv, g_table, part_ab, st),
+              "encode_backward");
+  }
+  return VIBO_OK;
+}
+
+int vibo_encode(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                const float* table, float* ability_mu, float* ability_logvar,
+                float* precision_sum, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!response || !mask || !table || !ability_mu || !ability_logvar)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (int rc = check_items(desc)) return rc;
+  if (desc->num_person == 0) return VIBO_OK;
+  VIBO_CUDA(vibo::launch_encode(*desc, response, mask, table, ability_mu, ability_logvar,
+                                precision_sum, static_cast<cudaStream_t>(stream)),
+            "encode");
+  return VIBO_OK;
+}
+
+int vibo_encode_backward(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                         const float* table, const float* ability_mu,
+                         const float* precision_sum, const float* g_ability_mu,
+                         const float* g_ability_logvar, float* g_table, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!response || !mask || !table || !ability_mu || !precision_sum || !g_ability_mu ||
+      !g_ability_logvar || !g_table)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (int rc = check_items(desc)) return rc;
+  if (workspace == nullptr || workspace_bytes < vibo_workspace_bytes(desc))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_workspace_bytes(desc)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const vibo_desc& d = *desc;
+  if (d.num_person == 0) {
+    VIBO_CUDA(cudaMemsetAsync(g_table, 0,
+                              sizeof(float) * 2 * (d.conditional ? d.num_item : 1) * 2 * d.ability_dim, st),
+              "memset");
+    return VIBO_OK;
+  }
+  Carve ws(workspace, workspace_bytes);
+  const size_t G = (size_t)vibo::sm_count() * 8;
+  float* part_ab = ws.take<float>(G * 2 * d.num_item * 2 * d.ability_dim);
+  VIBO_CUDA(vibo::launch_encode_bwd(d, response, mask, table, ability_mu, precision_sum,
+                                    g_ability_mu, g_ability_logvar, g_table, part_ab, st),
+            "encode_backward");
+  return VIBO_OK;
+}
+
+int vibo_link_loglik(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                     const float* ability, const float* item_feat, double* out_ll,
+                     float* g_ability, float* g_item, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!response || !mask || !ability || !item_feat || !out_ll)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if ((g_ability == nullptr) != (g_item == nullptr))
+    return fail(VIBO_ERR_BAD_ARGUMENT, "g_ability and g_item must both be given or both be NULL");
+  if (int rc = check_items(desc)) return rc;
+  if (workspace == nullptr || workspace_bytes < vibo_workspace_bytes(desc))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_workspace_bytes(desc)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const vibo_desc& d = *desc;
+  const size_t F = (size_t)vibo::item_width_host(d.irt_model, d.ability_dim);
+  if (d.num_person == 0) {
+    VIBO_CUDA(cudaMemsetAsync(out_ll, 0, sizeof(double), st), "memset");
+    if (g_item) VIBO_CUDA(cudaMemsetAsync(g_item, 0, sizeof(float) * d.num_item * F, st), "memset");
+    return VIBO_OK;
+  }
+  Carve ws(workspace, workspace_bytes);
+  const size_t G = (size_t)vibo::sm_count() * 8;
+  double* part_ll = ws.take<double>(G + 8);
+  float* part_g = ws.take<float>(G * d.num_item * F);
+  VIBO_CUDA(vibo::launch_link(d, response, mask, ability, item_feat, out_ll, g_ability, g_item,
+                              part_ll, part_g, st),
+            "link");
+  return VIBO_OK;
+}
+
+int vibo_decode(const vibo_desc* desc, const float* ability, const float* item_feat,
+                float* response_mu, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!ability || !item_feat || !response_mu) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (desc->num_person == 0) return VIBO_OK;
+  VIBO_CUDA(vibo::launch_decode(*desc, ability, item_feat, response_mu,
+                                static_cast<cudaStream_t>(stream)),
+            "decode");
+  return VIBO_OK;
+}
+
+int vibo_bernoulli_loglik(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                          const float* response_mu, double* out_ll, float* g_prob,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!response || !mask || !response_mu || !out_ll) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (workspace == nullptr || workspace_bytes < vibo_workspace_bytes(desc))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_workspace_bytes(desc)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (desc->num_person == 0) {
+    VIBO_CUDA(cudaMemsetAsync(out_ll, 0, sizeof(double), st), "memset");
+    return VIBO_OK;
+  }
+  Carve ws(workspace, workspace_bytes);
+  double* part_ll = ws.take<double>((size_t)vibo::sm_count() * 8 + 8);
+  VIBO_CUDA(vibo::launch_bernoulli_ll(*desc, response, mask, response_mu, out_ll, g_prob, part_ll, st),
+            "bernoulli_loglik");
+  return VIBO_OK;
+}
+
+}  // extern "C"

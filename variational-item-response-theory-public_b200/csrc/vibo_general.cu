@@ -1,0 +1,585 @@
+// General (decomposed) kernels of the VIBO ELBO path: encode, encode-backward,
+// link + log-likelihood, decode, Bernoulli log-likelihood on a materialised
+// response_mu.  They cover every variant (1/2/3PL, D <= 8, conditional or not,
+// missing data with prior experts or dropped) and back the module API pieces
+// (encode / decode / elbo / flows).  The single-pass fused kernel for the
+// headline configuration lives in vibo_fused.cu.
+//
+// Layout ("row-slab"): a CTA has NS warps; warp w owns the item slab
+// [w*32*M, (w+1)*32*M) -- lane l owns items w*32*M + m*32 + l, m < M -- for
+// EVERY row the CTA processes, so per-item quantities (item parameters, expert
+// table entries, per-item gradient accumulators) live in registers for the
+// whole kernel and cross-person sums need no atomics.  Per-row quantities are
+// combined across the NS slabs through shared memory in a fixed order
+// (deterministic).  CTAs are persistent over row tiles; per-CTA partials go to
+// the workspace and a small second kernel reduces them in a fixed order.
+#include "vibo_common.cuh"
+#include "vibo_kernels.h"
+
+namespace vibo {
+
+constexpr int kRowsPerTile = 8;
+
+__device__ __forceinline__ void block_sum_to(double v, double* dst) {
+  __shared__ double s_part[32];
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+    *dst = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// encode: product-of-experts sums (models.py:596-629, utils.py:105-113)
+// ---------------------------------------------------------------------------
+template <int D, int M>
+__global__ void __launch_bounds__(512) encode_kernel(int64_t P, int I, int cond, int missing_policy,
+                                                       const float* __restrict__ resp,
+                                                       const uint8_t* __restrict__ mask,
+                                                       const float* __restrict__ table,
+                                                       float* __restrict__ out_mu,
+                                                       float* __restrict__ out_lv,
+                                                       float* __restrict__ out_S) {
+  extern __shared__ float red[];  // [kRowsPerTile][NS][2D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NS = blockDim.x >> 5;
+  int j[M];
+  float tau[M][2][D], mt[M][2][D];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    j[m] = (warp * M + m) * 32 + lane;
+    const int jt = cond ? min(j[m], I - 1) : 0;
+    const int It = cond ? I : 1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float mu = table[((size_t)r * It + jt) * 2 * D + d];
+        const float lam = table[((size_t)r * It + jt) * 2 * D + D + d];
+        const float t = 1.0f / (expf(lam) + kPoeEps);
+        tau[m][r][d] = t;
+        mt[m][r][d] = mu * t;
+      }
+  }
+  const float prior_tau = (missing_policy == 0) ? 1.0f / (1.0f + kPoeEps) : 0.0f;
+  const int64_t n_tiles = (P + kRowsPerTile - 1) / kRowsPerTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 2
+    for (int rt = 0; rt < kRowsPerTile; ++rt) {
+      const int64_t row = tile * kRowsPerTile + rt;
+      if (row >= P) break;
+      float S[D], N[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) S[d] = N[d] = 0.0f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        if (j[m] < I) {
+          const float x = resp[row * I + j[m]];
+          const bool o = mask[row * I + j[m]] != 0;
+          const bool x1 = x > 0.5f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            S[d] += o ? (x1 ? tau[m][1][d] : tau[m][0][d]) : prior_tau;
+            N[d] += o ? (x1 ? mt[m][1][d] : mt[m][0][d]) : 0.0f;
+          }
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float s = warp_sum(S[d]), n = warp_sum(N[d]);
+        if (lane == 0) {
+          red[(rt * NS + warp) * 2 * D + d] = s;
+          red[(rt * NS + warp) * 2 * D + D + d] = n;
+        }
+      }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kRowsPerTile * D; t += blockDim.x) {
+      const int rt = t / D, d = t % D;
+      const int64_t row = tile * kRowsPerTile + rt;
+      if (row < P) {
+        float s = 0.0f, n = 0.0f;
+        for (int w = 0; w < NS; ++w) {
+          s += red[(rt * NS + w) * 2 * D + d];
+          n += red[(rt * NS + w) * 2 * D + D + d];
+        }
+        out_mu[row * D + d] = n / s;
+        out_lv[row * D + d] = logf(1.0f / s);
+        if (out_S) out_S[row * D + d] = s;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// encode backward: scatter per-person (GN, GS) into per-(r, item) sums
+// ---------------------------------------------------------------------------
+template <int D, int M>
+__global__ void __launch_bounds__(512) encode_bwd_kernel(int64_t P, int I, const float* __restrict__ resp,
+                                                           const uint8_t* __restrict__ mask,
+                                                           const float* __restrict__ amu,
+                                                           const float* __restrict__ Ssum,
+                                                           const float* __restrict__ g_mu,
+                                                           const float* __restrict__ g_lv,
+                                                           float* __restrict__ part /*[grid][2][I][2D] (A|B)*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int j[M];
+  float A[M][2][D], B[M][2][D];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    j[m] = (warp * M + m) * 32 + lane;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) A[m][r][d] = B[m][r][d] = 0.0f;
+  }
+  const int64_t n_tiles = (P + kRowsPerTile - 1) / kRowsPerTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 2
+    for (int rt = 0; rt < kRowsPerTile; ++rt) {
+      const int64_t row = tile * kRowsPerTile + rt;
+      if (row >= P) break;
+      float GN[D], GS[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float s = Ssum[row * D + d];
+        const float gm = g_mu[row * D + d];
+        GN[d] = gm / s;
+        GS[d] = -(gm * amu[row * D + d] + g_lv[row * D + d]) / s;
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        if (j[m] < I) {
+          const float x = resp[row * I + j[m]];
+          const bool o = mask[row * I + j[m]] != 0;
+          const bool x1 = x > 0.5f;
+          if (o) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              if (x1) {
+                A[m][1][d] += GN[d];
+                B[m][1][d] += GS[d];
+              } else {
+                A[m][0][d] += GN[d];
+                B[m][0][d] += GS[d];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  float* dst = part + (size_t)blockIdx.x * 2 * I * 2 * D;
+#pragma unroll
+  for (int m = 0; m < M; ++m)
+    if (j[m] < I) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          dst[((size_t)r * I + j[m]) * 2 * D + d] = A[m][r][d];
+          dst[((size_t)r * I + j[m]) * 2 * D + D + d] = B[m][r][d];
+        }
+    }
+}
+
+// Reduce the per-CTA (A, B) partials in a fixed order and apply the expert
+// chain rule: d/d mu = tau A ; d/d lam = (mu A + B) (-exp(lam) tau^2).
+// Unconditional tables additionally sum over items.
+__global__ void encode_bwd_finalize_kernel(int I, int D, int cond, int nparts,
+                                           const float* __restrict__ part,
+                                           const float* __restrict__ table,
+                                           float* __restrict__ g_table) {
+  const int It = cond ? I : 1;
+  const int n = 2 * It * D;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int d = t % D, jt = (t / D) % It, r = t / (D * It);
+    double a = 0.0, b = 0.0;
+    const int j0 = cond ? jt : 0, j1 = cond ? jt + 1 : I;
+    for (int p = 0; p < nparts; ++p) {
+      const float* src = part + (size_t)p * 2 * I * 2 * D;
+      for (int j = j0; j < j1; ++j) {
+        a += src[((size_t)r * I + j) * 2 * D + d];
+        b += src[((size_t)r * I + j) * 2 * D + D + d];
+      }
+    }
+    const float mu = table[((size_t)r * It + jt) * 2 * D + d];
+    const float lam = table[((size_t)r * It + jt) * 2 * D + D + d];
+    const float el = expf(lam);
+    const float tau = 1.0f / (el + kPoeEps);
+    g_table[((size_t)r * It + jt) * 2 * D + d] = tau * (float)a;
+    g_table[((size_t)r * It + jt) * 2 * D + D + d] = (mu * (float)a + (float)b) * (-el * tau * tau);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// link + log-likelihood (models.py:729-766, utils.py:46-49, models.py:399)
+// ---------------------------------------------------------------------------
+template <int D, int MODEL, int M, bool GRAD>
+__global__ void __launch_bounds__(512) link_kernel(int64_t P, int I, const float* __restrict__ resp,
+                                                     const uint8_t* __restrict__ mask,
+                                                     const float* __restrict__ ability,
+                                                     const float* __restrict__ item_feat,
+                                                     double* __restrict__ part_ll,
+                                                     float* __restrict__ g_ability,
+                                                     float* __restrict__ part_gitem /*[grid][I*F]*/) {
+  constexpr int F = item_width(MODEL, D);
+  constexpr int DA = MODEL == 1 ? 1 : D;  // discrimination width
+  extern __shared__ float red[];          // [kRowsPerTile][NS][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NS = blockDim.x >> 5;
+  int j[M];
+  float a[M][DA], b[M], gs[M], acc[M][F];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    j[m] = (warp * M + m) * 32 + lane;
+    const int jj = min(j[m], I - 1);
+    if constexpr (MODEL == 1) {
+      b[m] = item_feat[jj];
+      a[m][0] = 0.0f;
+      gs[m] = 0.0f;
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) a[m][d] = item_feat[(size_t)jj * F + d];
+      b[m] = item_feat[(size_t)jj * F + D];
+      gs[m] = MODEL == 3 ? 1.0f / (1.0f + expf(-item_feat[(size_t)jj * F + D + 1])) : 0.0f;
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[m][f] = 0.0f;
+  }
+  double ll_acc = 0.0;
+  const int64_t n_tiles = (P + kRowsPerTile - 1) / kRowsPerTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 2
+    for (int rt = 0; rt < kRowsPerTile; ++rt) {
+      const int64_t row = tile * kRowsPerTile + rt;
+      if (row >= P) break;
+      float th[D], gth[D];
+      float tsum = 0.0f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        th[d] = ability[row * D + d];
+        tsum += th[d];
+        gth[d] = 0.0f;
+      }
+      float ll_row = 0.0f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        if (j[m] < I) {
+          const float x = resp[row * I + j[m]];
+          const bool o = mask[row * I + j[m]] != 0;
+          if (o) {
+            float z = b[m];
+            if constexpr (MODEL == 1) {
+              z += tsum;
+            } else {
+#pragma unroll
+              for (int d = 0; d < D; ++d) z = fmaf(-th[d], a[m][d], z);
+            }
+            CellGrad c;
+            if constexpr (MODEL == 3) c = cell_3pl<true>(z, gs[m], x > 0.5f);
+            else c = cell_logistic<true>(z, x > 0.5f);
+            ll_row += c.ll;
+            if (GRAD) {
+              if constexpr (MODEL == 1) {
+                gth[0] += c.dz;
+                acc[m][0] += c.dz;
+              } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                  gth[d] = fmaf(-c.dz, a[m][d], gth[d]);
+                  acc[m][d] = fmaf(-c.dz, th[d], acc[m][d]);
+                }
+                acc[m][D] += c.dz;
+                if constexpr (MODEL == 3) acc[m][D + 1] += c.dgam;
+              }
+            }
+          }
+        }
+      }
+      ll_acc += (double)ll_row;
+      if (GRAD) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float v = warp_sum(MODEL == 1 ? gth[0] : gth[d]);
+          if (lane == 0) red[(rt * NS + warp) * D + d] = v;
+        }
+      }
+    }
+    if (GRAD) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < kRowsPerTile * D; t += blockDim.x) {
+        const int rt = t / D, d = t % D;
+        const int64_t row = tile * kRowsPerTile + rt;
+        if (row < P) {
+          float v = 0.0f;
+          for (int w = 0; w < NS; ++w) v += red[(rt * NS + w) * D + d];
+          g_ability[row * D + d] = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (GRAD) {
+    float* dst = part_gitem + (size_t)blockIdx.x * I * F;
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+      if (j[m] < I) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) dst[(size_t)j[m] * F + f] = acc[m][f];
+      }
+  }
+  block_sum_to(ll_acc, part_ll + blockIdx.x);
+}
+
+// out[k] = scale * sum_p part[p][k], fixed order (deterministic).
+__global__ void sum_partials_f32_kernel(const float* __restrict__ part, int nparts, int n, float scale,
+                                        float* __restrict__ out) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * n + k];
+    out[k] = scale * (float)s;
+  }
+}
+
+__global__ void sum_partials_f64_kernel(const double* __restrict__ part, int nparts, int stride,
+                                        int ncols, double* __restrict__ out) {
+  const int c = threadIdx.x;
+  if (c < ncols) {
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * stride + c];
+    out[c] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// decode: response_mu (P, I)  (models.py:729-766)
+// ---------------------------------------------------------------------------
+template <int MODEL>
+__global__ void decode_kernel(int64_t P, int I, int D, const float* __restrict__ ability,
+                              const float* __restrict__ item_feat, float* __restrict__ out) {
+  const int F = item_width(MODEL, D);
+  const int64_t n = P * (int64_t)I;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = c / I;
+    const int j = (int)(c - row * I);
+    float z;
+    if (MODEL == 1) {
+      z = item_feat[j];
+      for (int d = 0; d < D; ++d) z += ability[row * D + d];
+    } else {
+      z = item_feat[(size_t)j * F + D];
+      for (int d = 0; d < D; ++d) z = fmaf(-ability[row * D + d], item_feat[(size_t)j * F + d], z);
+    }
+    const float s = 1.0f / (1.0f + expf(-z));
+    if (MODEL == 3) {
+      const float g = 1.0f / (1.0f + expf(-item_feat[(size_t)j * F + D + 1]));
+      out[c] = fmaf(1.0f - g, s, g);
+    } else {
+      out[c] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// masked Bernoulli log-likelihood of a materialised response_mu (utils.py:46-49)
+// ---------------------------------------------------------------------------
+__global__ void bernoulli_ll_kernel(int64_t n, const float* __restrict__ resp,
+                                    const uint8_t* __restrict__ mask, const float* __restrict__ prob,
+                                    double* __restrict__ part_ll, float* __restrict__ g_prob) {
+  double acc = 0.0;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const bool o = mask[c] != 0;
+    const bool x1 = resp[c] > 0.5f;
+    const float p = prob[c];
+    const float pc = fminf(fmaxf(p, kEps32), 1.0f - kEps32);
+    const bool inside = (p >= kEps32) && (p <= 1.0f - kEps32);
+    const float ll = x1 ? logf(pc) : log1pf(-pc);
+    if (o) acc += (double)ll;
+    if (g_prob) g_prob[c] = (o && inside) ? (x1 ? 1.0f / pc : -1.0f / (1.0f - pc)) : 0.0f;
+  }
+  block_sum_to(acc, part_ll + blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+static int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+static inline int slab_m(int D) { return D <= 4 ? 4 : 2; }
+
+int general_max_items(int D) { return 32 * slab_m(D) * 16; }  // NS <= 16 warps per CTA
+
+int general_grid(int64_t P, int I, int D) {
+  const int ns = (I + 32 * slab_m(D) - 1) / (32 * slab_m(D));
+  const int ctas_per_sm = ns >= 16 ? 1 : (ns >= 8 ? 2 : (ns >= 4 ? 4 : 8));
+  const int64_t tiles = (P + kRowsPerTile - 1) / kRowsPerTile;
+  int64_t g = (int64_t)sm_count() * ctas_per_sm;
+  if (g > tiles) g = tiles;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <int D>
+static cudaError_t launch_encode_d(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                   const float* table, float* mu, float* lv, float* S,
+                                   cudaStream_t st) {
+  constexpr int M = D <= 4 ? 4 : 2;
+  const int ns = (d.num_item + 32 * M - 1) / (32 * M);
+  const int grid = general_grid(d.num_person, d.num_item, D);
+  const size_t smem = (size_t)kRowsPerTile * ns * 2 * D * sizeof(float);
+  encode_kernel<D, M><<<grid, ns * 32, smem, st>>>(d.num_person, d.num_item, d.conditional,
+                                                   d.missing_policy, resp, mask, table, mu, lv, S);
+  return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t launch_encode_bwd_d(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                       const float* table, const float* amu, const float* S,
+                                       const float* g_mu, const float* g_lv, float* g_table,
+                                       float* part, cudaStream_t st) {
+  constexpr int M = D <= 4 ? 4 : 2;
+  const int ns = (d.num_item + 32 * M - 1) / (32 * M);
+  const int grid = general_grid(d.num_person, d.num_item, D);
+  encode_bwd_kernel<D, M><<<grid, ns * 32, 0, st>>>(d.num_person, d.num_item, resp, mask, amu, S,
+                                                    g_mu, g_lv, part);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int n = 2 * (d.conditional ? d.num_item : 1) * D;
+  encode_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(d.num_item, D, d.conditional, grid,
+                                                              part, table, g_table);
+  return cudaGetLastError();
+}
+
+template <int D, int MODEL>
+static cudaError_t launch_link_dm(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                  const float* ability, const float* item_feat, double* out_ll,
+                                  float* g_ability, float* g_item, double* part_ll, float* part_g,
+                                  cudaStream_t st) {
+  constexpr int M = D <= 4 ? 4 : 2;
+  constexpr int F = item_width(MODEL, D);
+  const int ns = (d.num_item + 32 * M - 1) / (32 * M);
+  const int grid = general_grid(d.num_person, d.num_item, D);
+  const size_t smem = (size_t)kRowsPerTile * ns * D * sizeof(float);
+  if (g_item != nullptr) {
+    link_kernel<D, MODEL, M, true><<<grid, ns * 32, smem, st>>>(
+        d.num_person, d.num_item, resp, mask, ability, item_feat, part_ll, g_ability, part_g);
+  } else {
+    link_kernel<D, MODEL, M, false><<<grid, ns * 32, smem, st>>>(
+        d.num_person, d.num_item, resp, mask, ability, item_feat, part_ll, nullptr, nullptr);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+  if (g_item != nullptr) {
+    const int n = d.num_item * F;
+    sum_partials_f32_kernel<<<(n + 127) / 128, 128, 0, st>>>(part_g, grid, n, 1.0f, g_item);
+  }
+  return cudaGetLastError();
+}
+
+#define VIBO_SWITCH_D(D_, ...)                      \
+  switch (D_) {                                     \
+    case 1: { constexpr int kD = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int kD = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int kD = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int kD = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int kD = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int kD = 6; __VA_ARGS__; } break; \
+    case 7: { constexpr int kD = 7; __VA_ARGS__; } break; \
+    case 8: { constexpr int kD = 8; __VA_ARGS__; } break; \
+    default: return cudaErrorInvalidValue;          \
+  }
+
+cudaError_t launch_encode(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                          const float* table, float* mu, float* lv, float* S, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  VIBO_SWITCH_D(d.ability_dim, e = launch_encode_d<kD>(d, resp, mask, table, mu, lv, S, st));
+  return e;
+}
+
+cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                              const float* table, const float* amu, const float* S,
+                              const float* g_mu, const float* g_lv, float* g_table, float* part,
+                              cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  VIBO_SWITCH_D(d.ability_dim,
+                e = launch_encode_bwd_d<kD>(d, resp, mask, table, amu, S, g_mu, g_lv, g_table, part, st));
+  return e;
+}
+
+cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                        const float* ability, const float* item_feat, double* out_ll,
+                        float* g_ability, float* g_item, double* part_ll, float* part_g,
+                        cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  switch (d.irt_model) {
+    case 1:
+      VIBO_SWITCH_D(d.ability_dim, e = (launch_link_dm<kD, 1>(d, resp, mask, ability, item_feat, out_ll,
+                                                            g_ability, g_item, part_ll, part_g, st)));
+      break;
+    case 2:
+      VIBO_SWITCH_D(d.ability_dim, e = (launch_link_dm<kD, 2>(d, resp, mask, ability, item_feat, out_ll,
+                                                            g_ability, g_item, part_ll, part_g, st)));
+      break;
+    case 3:
+      VIBO_SWITCH_D(d.ability_dim, e = (launch_link_dm<kD, 3>(d, resp, mask, ability, item_feat, out_ll,
+                                                            g_ability, g_item, part_ll, part_g, st)));
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return e;
+}
+
+cudaError_t launch_decode(const vibo_desc& d, const float* ability, const float* item_feat,
+                          float* out, cudaStream_t st) {
+  const int64_t n = d.num_person * (int64_t)d.num_item;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  switch (d.irt_model) {
+    case 1: decode_kernel<1><<<(int)blocks, 256, 0, st>>>(d.num_person, d.num_item, d.ability_dim, ability, item_feat, out); break;
+    case 2: decode_kernel<2><<<(int)blocks, 256, 0, st>>>(d.num_person, d.num_item, d.ability_dim, ability, item_feat, out); break;
+    case 3: decode_kernel<3><<<(int)blocks, 256, 0, st>>>(d.num_person, d.num_item, d.ability_dim, ability, item_feat, out); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+int bernoulli_grid(int64_t n) {
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+cudaError_t launch_bernoulli_ll(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                const float* prob, double* out_ll, float* g_prob, double* part_ll,
+                                cudaStream_t st) {
+  const int64_t n = d.num_person * (int64_t)d.num_item;
+  const int grid = bernoulli_grid(n);
+  bernoulli_ll_kernel<<<grid, 256, 0, st>>>(n, resp, mask, prob, part_ll, g_prob);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+  return cudaGetLastError();
+}
+
+}  // namespace vibo

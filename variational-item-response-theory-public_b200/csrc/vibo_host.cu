@@ -1,0 +1,136 @@
+// Host-buffer entry point: streams person chunks host->device on a private
+// copy stream, overlapped with the kernels of the previous chunk (double
+// buffered), and accumulates the per-chunk results on the device.  This is the
+// end-to-end path a caller with the reference's host-resident dataset arrays
+// (src/datasets.py:928-940) uses.
+#include <string>
+
+#include "vibo_kernels.h"
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct HostPipe {
+  cudaStream_t copy = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  cudaEvent_t consumed[2] = {nullptr, nullptr};
+  cudaEvent_t start = nullptr;
+  int device = -1;
+  cudaError_t ensure() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (copy != nullptr && dev == device) return cudaSuccess;
+    device = dev;
+    if ((e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int i = 0; i < 2; ++i) {
+      if ((e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    return cudaEventCreateWithFlags(&start, cudaEventDisableTiming);
+  }
+};
+thread_local HostPipe g_pipe;
+
+struct StagingLayout {
+  size_t resp[2], mask[2], scalars, g_table, g_item, total;
+};
+
+StagingLayout staging_layout(const vibo_desc& d, int64_t chunk) {
+  StagingLayout L;
+  const size_t cells = (size_t)chunk * d.num_item;
+  const size_t F = (size_t)vibo::item_width_host(d.irt_model, d.ability_dim);
+  size_t off = 0;
+  for (int b = 0; b < 2; ++b) {
+    L.resp[b] = off; off += align_up(cells * 4, 256);
+    L.mask[b] = off; off += align_up(cells, 256);
+  }
+  L.scalars = off; off += 256;
+  L.g_table = off; off += align_up(4 * 2 * (size_t)(d.conditional ? d.num_item : 1) * 2 * d.ability_dim, 256);
+  L.g_item = off; off += align_up(4 * (size_t)d.num_item * F, 256);
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t vibo_host_staging_bytes(const vibo_desc* desc, int64_t chunk_person) {
+  if (desc == nullptr || chunk_person <= 0) return 0;
+  return staging_layout(*desc, chunk_person).total;
+}
+
+int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
+                         const uint8_t* mask_host, const float* table, const float* item_feat,
+                         const float* eps_ability, uint64_t seed, float beta,
+                         double* out_scalars, double* out_scalars_host, float* g_table,
+                         float* g_item, int64_t chunk_person, void* staging,
+                         size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (desc == nullptr || response_host == nullptr || mask_host == nullptr || staging == nullptr ||
+      out_scalars == nullptr || chunk_person <= 0)
+    return VIBO_ERR_BAD_ARGUMENT;
+  const vibo_desc& d = *desc;
+  const StagingLayout L = staging_layout(d, chunk_person);
+  if (staging_bytes < L.total) return VIBO_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_pipe.ensure() != cudaSuccess) return VIBO_ERR_CUDA;
+  char* base = static_cast<char*>(staging);
+  double* tmp_scalars = reinterpret_cast<double*>(base + L.scalars);
+  float* tmp_g_table = reinterpret_cast<float*>(base + L.g_table);
+  float* tmp_g_item = reinterpret_cast<float*>(base + L.g_item);
+  const bool grad = g_item != nullptr;
+  const size_t F = (size_t)vibo::item_width_host(d.irt_model, d.ability_dim);
+  const int n_table = 2 * (d.conditional ? d.num_item : 1) * 2 * d.ability_dim;
+  const int n_item = (int)(d.num_item * F);
+
+  cudaMemsetAsync(out_scalars, 0, 2 * sizeof(double), st);
+  if (grad) {
+    cudaMemsetAsync(g_table, 0, sizeof(float) * n_table, st);
+    cudaMemsetAsync(g_item, 0, sizeof(float) * n_item, st);
+  }
+  // staging buffers may still be read by earlier work on `st`
+  cudaEventRecord(g_pipe.start, st);
+  cudaStreamWaitEvent(g_pipe.copy, g_pipe.start, 0);
+
+  int64_t c = 0;
+  for (int64_t r0 = 0; r0 < d.num_person; r0 += chunk_person, ++c) {
+    const int b = (int)(c & 1);
+    const int64_t n = (d.num_person - r0 < chunk_person) ? d.num_person - r0 : chunk_person;
+    if (c >= 2) cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0);
+    cudaMemcpyAsync(base + L.resp[b], response_host + (size_t)r0 * d.num_item,
+                    (size_t)n * d.num_item * sizeof(float), cudaMemcpyHostToDevice, g_pipe.copy);
+    cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item, (size_t)n * d.num_item,
+                    cudaMemcpyHostToDevice, g_pipe.copy);
+    cudaEventRecord(g_pipe.copied[b], g_pipe.copy);
+    cudaStreamWaitEvent(st, g_pipe.copied[b], 0);
+    vibo_desc dc = d;
+    dc.num_person = n;
+    dc.person_offset = d.person_offset + r0;
+    const int rc = vibo_fused_elbo(&dc, reinterpret_cast<const float*>(base + L.resp[b]),
+                                   reinterpret_cast<const uint8_t*>(base + L.mask[b]), table, item_feat,
+                                   eps_ability ? eps_ability + (size_t)r0 * d.ability_dim : nullptr, seed,
+                                   beta, tmp_scalars, nullptr, nullptr, nullptr,
+                                   grad ? tmp_g_table : nullptr, grad ? tmp_g_item : nullptr, workspace,
+                                   workspace_bytes, st);
+    if (rc != VIBO_OK) return rc;
+    if (grad) {
+      if (vibo::launch_accumulate(g_table, tmp_g_table, n_table, out_scalars, tmp_scalars, 2, st) != cudaSuccess)
+        return VIBO_ERR_CUDA;
+      if (vibo::launch_accumulate(g_item, tmp_g_item, n_item, nullptr, nullptr, 0, st) != cudaSuccess)
+        return VIBO_ERR_CUDA;
+    } else {
+      if (vibo::launch_accumulate(nullptr, nullptr, 0, out_scalars, tmp_scalars, 2, st) != cudaSuccess)
+        return VIBO_ERR_CUDA;
+    }
+    cudaEventRecord(g_pipe.consumed[b], st);
+  }
+  if (out_scalars_host != nullptr)
+    cudaMemcpyAsync(out_scalars_host, out_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return VIBO_ERR_CUDA;
+  return VIBO_OK;
+}
+
+}  // extern "C"

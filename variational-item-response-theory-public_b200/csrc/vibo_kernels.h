@@ -1,0 +1,60 @@
+// Internal launcher declarations shared by the .cu translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/vibo_b200.h"
+
+namespace vibo {
+
+int sm_count();
+int item_width_host(int model, int D);
+int general_max_items(int D);
+int general_grid(int64_t P, int I, int D);
+int bernoulli_grid(int64_t n);
+
+// vibo_general.cu
+cudaError_t launch_encode(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                          const float* table, float* mu, float* lv, float* S, cudaStream_t st);
+cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                              const float* table, const float* amu, const float* S,
+                              const float* g_mu, const float* g_lv, float* g_table, float* part,
+                              cudaStream_t st);
+cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                        const float* ability, const float* item_feat, double* out_ll,
+                        float* g_ability, float* g_item, double* part_ll, float* part_g,
+                        cudaStream_t st);
+cudaError_t launch_decode(const vibo_desc& d, const float* ability, const float* item_feat,
+                          float* out, cudaStream_t st);
+cudaError_t launch_bernoulli_ll(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                const float* prob, double* out_ll, float* g_prob, double* part_ll,
+                                cudaStream_t st);
+
+// vibo_person.cu: per-person prior / reparameterisation math of the
+// multi-pass composition of vibo_fused_elbo.
+int person_grid(int64_t P);
+cudaError_t launch_person_forward(const vibo_desc& d, const float* amu, const float* alv,
+                                  const float* eps_or_null, uint64_t seed, float* eps_out,
+                                  float* ability, double* part_term, double* out_term,
+                                  cudaStream_t st);
+cudaError_t launch_person_backward(const vibo_desc& d, float beta, const float* amu,
+                                   const float* alv, const float* eps, const float* ability,
+                                   const float* g_ll_ability, float* g_mu, float* g_lv,
+                                   cudaStream_t st);
+cudaError_t launch_negate(float* v, int n, cudaStream_t st);
+cudaError_t launch_accumulate(float* dst, const float* src, int n, double* dst2, const double* src2,
+                              int n2, cudaStream_t st);
+
+// vibo_fused.cu: single-pass kernel.  Returns false when the configuration is
+// not covered (caller composes the general kernels instead).
+bool fused_supported(const vibo_desc& d, const float* resp, const uint8_t* mask);
+size_t fused_workspace_bytes(const vibo_desc& d);
+cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                         const float* table, const float* item_feat, const float* eps,
+                         uint64_t seed, float beta, double* out_scalars, float* amu, float* alv,
+                         float* ability, float* g_table, float* g_item, void* ws, size_t ws_bytes,
+                         bool accumulate, cudaStream_t st);
+
+}  // namespace vibo

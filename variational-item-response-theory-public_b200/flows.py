@@ -1,0 +1,45 @@
+"""Planar normalizing flows on the (P, D) abilities and (I, F) item features
+(``--n-norm-flows``).  Parameter containers and state_dict keys match the
+reference (src/torch_core/flows.py:6-66: ``flows.{k}.{u,w,b}``, u, w ~ N(0, 1),
+b = 1) so reference checkpoints load; the math is per-person / per-item and
+tiny, so it stays in PyTorch autograd around the kernels.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class PlanarFlow(nn.Module):
+    """f(z) = z + u_hat tanh(w.z + b) with u_hat made invertible
+    (Rezende & Mohamed 2015); reference flows.py:21-41."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self.u = nn.Parameter(torch.randn(in_features))
+        self.w = nn.Parameter(torch.randn(in_features))
+        self.b = nn.Parameter(torch.ones(1))
+
+    def forward(self, z):
+        w, u = self.w, self.u
+        uw = (u * w).sum()
+        u_hat = u + (F.softplus(uw) - 1.0 - uw) * w / (w * w).sum()
+        h = torch.tanh(z @ w + self.b)
+        f_z = z + h.unsqueeze(1) * u_hat.unsqueeze(0)
+        slope = (1.0 - h * h) * (w * u_hat).sum()
+        return f_z, torch.log(torch.abs(1.0 + slope) + 1e-8)
+
+
+class NormalizingFlows(nn.Module):
+    """K planar flows in sequence; returns (z_K, sum_k log|det J_k|),
+    reference flows.py:58-66."""
+
+    def __init__(self, in_features, flow_type=PlanarFlow, n_flows=1):
+        super().__init__()
+        self.flows = nn.ModuleList([flow_type(in_features) for _ in range(n_flows)])
+
+    def forward(self, z):
+        total = 0
+        for flow in self.flows:
+            z, ldj = flow(z)
+            total = total + ldj
+        return z, total

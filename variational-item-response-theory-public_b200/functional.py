@@ -1,0 +1,171 @@
+"""Autograd bindings of the VIBO kernels.
+
+Each Function wraps one C-ABI entry point (through ``kernels``) so that the
+small parameter-side chains -- encoder MLP on the 2 / 2*I expert rows, item
+reparameterisation, planar flows, item KL -- stay ordinary PyTorch autograd on
+tiny tensors, while everything that touches the (P, I) response matrix runs in
+the CUDA kernels.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as K
+
+ELBO_KL, ELBO_SAMPLE = K.ELBO_KL, K.ELBO_SAMPLE
+MISSING_PRIOR, MISSING_DROP = K.MISSING_PRIOR, K.MISSING_DROP
+
+
+def prepare_rows(response: torch.Tensor, mask: torch.Tensor):
+    """(P, I, 1) float response + any-dtype mask -> (P, I) float32 and (P, I)
+    uint8 views the kernels read.  bool/uint8 masks are reinterpreted without a
+    copy; the int64 mask the reference CLI builds (vibo.py:240) costs one
+    conversion pass."""
+    if response.dim() == 3:
+        response = response.reshape(response.shape[0], response.shape[1])
+    if mask.dim() == 3:
+        mask = mask.reshape(mask.shape[0], mask.shape[1])
+    if response.dtype != torch.float32:
+        response = response.float()
+    response = response.contiguous()
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    elif mask.dtype != torch.uint8:
+        mask = (mask != 0).to(torch.uint8)
+    return response, mask.contiguous()
+
+
+class FusedElbo(torch.autograd.Function):
+    """loss_k = -LL + beta*KL_theta (KL form) or -LL - sum(log p - log q)(theta)
+    (sample form), one pass over the rows (vibo_fused_elbo)."""
+
+    @staticmethod
+    def forward(ctx, response, mask, table, item_feat, eps_ability, cfg):
+        want = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        out = K.fused_elbo(response, mask, table.detach().contiguous(),
+                           item_feat.detach().contiguous(), eps_ability,
+                           irt_model=cfg["irt_model"], conditional=cfg["conditional"],
+                           missing_policy=cfg["missing_policy"], elbo_form=cfg["elbo_form"],
+                           beta=cfg["beta"], seed=cfg.get("seed", 0),
+                           person_offset=cfg.get("person_offset", 0), want_grads=want,
+                           want_person_outputs=cfg.get("want_person_outputs", False))
+        ll, term = out["scalars"][0], out["scalars"][1]
+        if cfg["elbo_form"] == ELBO_KL:
+            loss_k = -ll + cfg["beta"] * term
+        else:
+            loss_k = -ll - term
+        if want:
+            ctx.save_for_backward(out["g_table"], out["g_item"])
+        extras = [out["scalars"]]
+        for name in ("ability_mu", "ability_logvar", "ability"):
+            extras.append(out[name] if out[name] is not None else torch.empty(0, device=response.device))
+        ctx.mark_non_differentiable(*extras)
+        return (loss_k.to(torch.float32), *extras)
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        g_table, g_item = ctx.saved_tensors
+        return None, None, g_loss * g_table, g_loss * g_item, None, None
+
+
+class EncodePosterior(torch.autograd.Function):
+    """(ability_mu, ability_logvar) = PoE over each person's experts
+    (vibo_encode / vibo_encode_backward)."""
+
+    @staticmethod
+    def forward(ctx, response, mask, table, conditional, missing_policy):
+        tbl = table.detach().contiguous()
+        mu, lv, S = K.encode(response, mask, tbl, conditional=conditional, missing_policy=missing_policy)
+        ctx.save_for_backward(response, mask, tbl, mu, S)
+        ctx.cfg = (conditional, missing_policy)
+        return mu, lv
+
+    @staticmethod
+    def backward(ctx, g_mu, g_lv):
+        response, mask, tbl, mu, S = ctx.saved_tensors
+        conditional, missing_policy = ctx.cfg
+        g_table = K.encode_backward(response, mask, tbl, mu, S, g_mu.contiguous(), g_lv.contiguous(),
+                                    conditional=conditional, missing_policy=missing_policy)
+        return None, None, g_table, None, None
+
+
+class LinkLogLik(torch.autograd.Function):
+    """LL = sum_ij o_ij log Bernoulli(x_ij; irt(ability, item_feat)) without
+    materialising response_mu (vibo_link_loglik).  Gradients are produced in
+    the same pass as the value."""
+
+    @staticmethod
+    def forward(ctx, response, mask, ability, item_feat, irt_model):
+        want = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        ll, g_ab, g_it = K.link_loglik(response, mask, ability.detach().contiguous(),
+                                       item_feat.detach().contiguous(), irt_model=irt_model,
+                                       want_grads=want)
+        if want:
+            ctx.save_for_backward(g_ab, g_it)
+        return ll[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        g_ab, g_it = ctx.saved_tensors
+        return None, None, g * g_ab, g * g_it, None
+
+
+class Decode(torch.autograd.Function):
+    """response_mu (P, I, 1) = irt_model_{1,2,3}pl(ability, item_feat)
+    (vibo_decode).  API-parity path: the backward re-derives the link with
+    dense torch ops since a materialised (P, I) gradient arrives anyway."""
+
+    @staticmethod
+    def forward(ctx, ability, item_feat, irt_model):
+        out = K.decode(ability.detach().contiguous(), item_feat.detach().contiguous(), irt_model=irt_model)
+        ctx.save_for_backward(ability, item_feat)
+        ctx.irt_model = irt_model
+        return out.unsqueeze(2)
+
+    @staticmethod
+    def backward(ctx, g):
+        ability, item_feat = ctx.saved_tensors
+        m = ctx.irt_model
+        D = ability.shape[1]
+        g = g.reshape(g.shape[0], g.shape[1])
+        if m == 1:
+            z = ability.sum(1, keepdim=True) + item_feat[:, 0][None, :]
+        else:
+            z = ability @ (-item_feat[:, :D].T) + item_feat[:, D][None, :]
+        s = torch.sigmoid(z)
+        g_item = torch.zeros_like(item_feat)
+        if m == 3:
+            guess = torch.sigmoid(item_feat[:, D + 1])
+            gz = g * (1 - guess)[None, :] * s * (1 - s)
+            g_item[:, D + 1] = (g * (1 - s)).sum(0) * guess * (1 - guess)
+        else:
+            gz = g * s * (1 - s)
+        if m == 1:
+            g_ability = gz.sum(1, keepdim=True).expand(-1, D).contiguous()
+            g_item[:, 0] = gz.sum(0)
+        else:
+            g_ability = -(gz @ item_feat[:, :D])
+            g_item[:, :D] = -(gz.T @ ability)
+            g_item[:, D] = gz.sum(0)
+        return g_ability, g_item, None
+
+
+class BernoulliLogLik(torch.autograd.Function):
+    """masked_bernoulli_log_pdf(response, mask, response_mu).sum() on a
+    materialised response_mu (vibo_bernoulli_loglik)."""
+
+    @staticmethod
+    def forward(ctx, response, mask, response_mu):
+        want = bool(ctx.needs_input_grad[2])
+        shape = response_mu.shape
+        mu2 = response_mu.detach().reshape(response.shape).contiguous()
+        ll, g = K.bernoulli_loglik(response, mask, mu2, want_grad=want)
+        if want:
+            ctx.save_for_backward(g)
+        ctx.shape = shape
+        return ll[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return None, None, (gl * g).reshape(ctx.shape)

@@ -1,0 +1,201 @@
+"""Tensor-level wrappers of the C ABI (one Python function per entry point).
+
+Every function takes/returns CUDA tensors, enqueues on the current torch
+stream and never synchronises.  ``tests/`` swaps this module's functions for a
+numpy oracle to exercise the host logic on machines without a GPU; the product
+itself has no such fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import Desc, ELBO_KL, ELBO_SAMPLE, MISSING_DROP, MISSING_PRIOR  # noqa: F401
+
+_workspaces = {}
+
+
+def item_feat_width(irt_model: int, ability_dim: int) -> int:
+    return {1: 1, 2: ability_dim + 1, 3: ability_dim + 2}[irt_model]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_rows(response: torch.Tensor, mask: torch.Tensor):
+    if not response.is_cuda:
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    assert response.dtype == torch.float32 and response.dim() == 2 and response.is_contiguous()
+    assert mask.dtype == torch.uint8 and mask.shape == response.shape and mask.is_contiguous()
+
+
+def make_desc(P, I, D, irt_model, conditional, missing_policy=MISSING_PRIOR, elbo_form=ELBO_KL,
+              person_offset=0) -> Desc:
+    return Desc(int(P), int(I), int(D), int(irt_model), int(bool(conditional)), int(missing_policy),
+                int(elbo_form), int(person_offset))
+
+
+def workspace(desc: Desc, device) -> torch.Tensor:
+    """Per-(device, stream) scratch, grown on demand and reused across calls."""
+    need = int(_lib.load().vibo_workspace_bytes(C.byref(desc)))
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def fused_elbo(response, mask, table, item_feat, eps_ability, *, irt_model, conditional,
+               missing_policy=MISSING_PRIOR, elbo_form=ELBO_KL, beta=1.0, seed=0, person_offset=0,
+               want_grads=True, want_person_outputs=False):
+    """vibo_fused_elbo.  Returns dict(scalars (2,) f64 [LL, person_term],
+    g_table, g_item (or None), ability_mu/ability_logvar/ability (or None))."""
+    _check_rows(response, mask)
+    lib = _lib.load()
+    P, I = response.shape
+    D = table.shape[-1] // 2
+    dev = response.device
+    desc = make_desc(P, I, D, irt_model, conditional, missing_policy, elbo_form, person_offset)
+    F = item_feat_width(irt_model, D)
+    assert table.shape == (2, I if conditional else 1, 2 * D) and table.is_contiguous()
+    assert item_feat.shape == (I, F) and item_feat.is_contiguous()
+    assert table.dtype == torch.float32 and item_feat.dtype == torch.float32
+    if eps_ability is not None:
+        assert eps_ability.shape == (P, D) and eps_ability.is_contiguous()
+        assert eps_ability.dtype == torch.float32
+    scalars = torch.empty(2, dtype=torch.float64, device=dev)
+    g_table = torch.empty_like(table) if want_grads else None
+    g_item = torch.empty_like(item_feat) if want_grads else None
+    amu = alv = th = None
+    if want_person_outputs:
+        amu = torch.empty(P, D, dtype=torch.float32, device=dev)
+        alv = torch.empty_like(amu)
+        th = torch.empty_like(amu)
+    ws = workspace(desc, dev)
+    rc = lib.vibo_fused_elbo(C.byref(desc), _ptr(response), _ptr(mask), _ptr(table), _ptr(item_feat),
+                             _ptr(eps_ability), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(beta),
+                             _ptr(scalars), _ptr(amu), _ptr(alv), _ptr(th), _ptr(g_table), _ptr(g_item),
+                             _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "vibo_fused_elbo")
+    return dict(scalars=scalars, g_table=g_table, g_item=g_item, ability_mu=amu,
+                ability_logvar=alv, ability=th)
+
+
+def fused_elbo_host(response_host, mask_host, table, item_feat, eps_ability, *, irt_model,
+                    conditional, missing_policy=MISSING_PRIOR, elbo_form=ELBO_KL, beta=1.0, seed=0,
+                    person_offset=0, want_grads=True, chunk_person=65536, staging=None):
+    """vibo_fused_elbo_host: response/mask are HOST tensors (pinned for full
+    copy bandwidth); returns the same dict as fused_elbo plus ``scalars_host``."""
+    lib = _lib.load()
+    assert not response_host.is_cuda and not mask_host.is_cuda
+    assert response_host.dtype == torch.float32 and response_host.is_contiguous()
+    assert mask_host.dtype == torch.uint8 and mask_host.is_contiguous()
+    P, I = response_host.shape
+    D = table.shape[-1] // 2
+    dev = table.device
+    chunk_person = int(min(chunk_person, max(P, 1)))
+    desc = make_desc(P, I, D, irt_model, conditional, missing_policy, elbo_form, person_offset)
+    need = int(lib.vibo_host_staging_bytes(C.byref(desc), chunk_person))
+    if staging is None or staging.numel() < need:
+        staging = torch.empty(need, dtype=torch.uint8, device=dev)
+    scalars = torch.empty(2, dtype=torch.float64, device=dev)
+    scalars_host = torch.empty(2, dtype=torch.float64).pin_memory()
+    g_table = torch.empty_like(table) if want_grads else None
+    g_item = torch.empty_like(item_feat) if want_grads else None
+    ws = workspace(desc, dev)
+    rc = lib.vibo_fused_elbo_host(C.byref(desc), _ptr(response_host), _ptr(mask_host), _ptr(table),
+                                  _ptr(item_feat), _ptr(eps_ability),
+                                  C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(beta), _ptr(scalars),
+                                  _ptr(scalars_host), _ptr(g_table), _ptr(g_item),
+                                  C.c_int64(chunk_person), _ptr(staging), staging.numel(), _ptr(ws),
+                                  ws.numel(), _stream(dev))
+    _lib.check(rc, "vibo_fused_elbo_host")
+    return dict(scalars=scalars, scalars_host=scalars_host, g_table=g_table, g_item=g_item,
+                staging=staging)
+
+
+def encode(response, mask, table, *, conditional, missing_policy=MISSING_PRIOR):
+    """vibo_encode -> (ability_mu, ability_logvar, precision_sum), each (P, D)."""
+    _check_rows(response, mask)
+    P, I = response.shape
+    D = table.shape[-1] // 2
+    desc = make_desc(P, I, D, 1, conditional, missing_policy)
+    mu = torch.empty(P, D, dtype=torch.float32, device=response.device)
+    lv = torch.empty_like(mu)
+    S = torch.empty_like(mu)
+    rc = _lib.load().vibo_encode(C.byref(desc), _ptr(response), _ptr(mask), _ptr(table.contiguous()),
+                                 _ptr(mu), _ptr(lv), _ptr(S), _stream(response.device))
+    _lib.check(rc, "vibo_encode")
+    return mu, lv, S
+
+
+def encode_backward(response, mask, table, ability_mu, precision_sum, g_mu, g_logvar, *,
+                    conditional, missing_policy=MISSING_PRIOR):
+    """vibo_encode_backward -> g_table (2, It, 2D)."""
+    _check_rows(response, mask)
+    P, I = response.shape
+    D = table.shape[-1] // 2
+    desc = make_desc(P, I, D, 1, conditional, missing_policy)
+    g_table = torch.empty_like(table)
+    ws = workspace(desc, response.device)
+    rc = _lib.load().vibo_encode_backward(
+        C.byref(desc), _ptr(response), _ptr(mask), _ptr(table), _ptr(ability_mu), _ptr(precision_sum),
+        _ptr(g_mu.contiguous()), _ptr(g_logvar.contiguous()), _ptr(g_table), _ptr(ws), ws.numel(),
+        _stream(response.device))
+    _lib.check(rc, "vibo_encode_backward")
+    return g_table
+
+
+def link_loglik(response, mask, ability, item_feat, *, irt_model, want_grads=True):
+    """vibo_link_loglik -> (ll (1,) f64, dLL/d ability or None, dLL/d item_feat or None)."""
+    _check_rows(response, mask)
+    P, I = response.shape
+    D = ability.shape[1]
+    desc = make_desc(P, I, D, irt_model, 0)
+    ll = torch.empty(1, dtype=torch.float64, device=response.device)
+    g_ab = torch.empty_like(ability) if want_grads else None
+    g_it = torch.empty_like(item_feat) if want_grads else None
+    ws = workspace(desc, response.device)
+    rc = _lib.load().vibo_link_loglik(C.byref(desc), _ptr(response), _ptr(mask), _ptr(ability),
+                                      _ptr(item_feat), _ptr(ll), _ptr(g_ab), _ptr(g_it), _ptr(ws),
+                                      ws.numel(), _stream(response.device))
+    _lib.check(rc, "vibo_link_loglik")
+    return ll, g_ab, g_it
+
+
+def decode(ability, item_feat, *, irt_model):
+    """vibo_decode -> response_mu (P, I)."""
+    if not ability.is_cuda:
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    P, D = ability.shape
+    I = item_feat.shape[0]
+    desc = make_desc(P, I, D, irt_model, 0)
+    out = torch.empty(P, I, dtype=torch.float32, device=ability.device)
+    rc = _lib.load().vibo_decode(C.byref(desc), _ptr(ability), _ptr(item_feat), _ptr(out),
+                                 _stream(ability.device))
+    _lib.check(rc, "vibo_decode")
+    return out
+
+
+def bernoulli_loglik(response, mask, response_mu, *, want_grad=True):
+    """vibo_bernoulli_loglik -> (ll (1,) f64, dLL/d response_mu (P, I) or None)."""
+    _check_rows(response, mask)
+    P, I = response.shape
+    desc = make_desc(P, I, 1, 1, 0)
+    ll = torch.empty(1, dtype=torch.float64, device=response.device)
+    g = torch.empty_like(response_mu) if want_grad else None
+    ws = workspace(desc, response.device)
+    rc = _lib.load().vibo_bernoulli_loglik(C.byref(desc), _ptr(response), _ptr(mask), _ptr(response_mu),
+                                           _ptr(ll), _ptr(g), _ptr(ws), ws.numel(),
+                                           _stream(response.device))
+    _lib.check(rc, "vibo_bernoulli_loglik")
+    return ll, g
