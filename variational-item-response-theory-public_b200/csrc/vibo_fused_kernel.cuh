@@ -1,0 +1,592 @@
+// Single-pass fused ELBO kernel for the unconditional encoder (sm_100a).
+//
+// One pass over the (P, I) response + mask rows computes, per person,
+//   counts -> product-of-experts posterior (models.py:596-629, utils.py:105-113)
+//   theta = mu + sd * eps                 (models.py:506-510)
+//   z_ij, masked Bernoulli log-lik       (models.py:729-766, utils.py:46-49)
+//   KL(q||N(0,1)) or log p - log q       (utils.py:85-88 / models.py:433-435)
+// and, when GRAD, d loss_k / d item_feat and d loss_k / d table in the same
+// read of the rows (SURVEY.md Appendix A "Backward").
+//
+// Data movement: chunks of R rows (R % 16 == 0, so the float32 response block,
+// the uint8 mask block and the eps block all start 16-byte aligned whatever I
+// is) stream into a ring of shared-memory stages with 1-D TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) completing on mbarriers.  There is no dedicated
+// producer warp (a 17th warp would cap registers at 96/thread): the warp that
+// is LAST to finish a stage re-arms that stage's barrier and issues the copy
+// of the chunk that will next occupy it, so the refill starts the moment the
+// slot is free.  The warps read their rows with conflict-free 128-bit LDS;
+// each row is read from HBM exactly once.
+//
+// Work layout: a sub-group of LPP lanes owns one person (32/LPP persons per
+// warp at a time).  Lane q of the sub-group owns the 4-item groups
+// g = q + LPP*k (k < NG), i.e. items 4g..4g+3, for EVERY person the warp
+// processes, so item parameters come from shared memory as float4 and the
+// per-item gradient accumulators stay in registers for the whole kernel: the
+// cross-person reductions need no atomics and the result is deterministic.
+#pragma once
+
+#include "vibo_common.cuh"
+#include "vibo_kernels.h"
+
+namespace vibo {
+
+constexpr int kFusedConsumerWarps = 16;
+constexpr int kFusedThreads = kFusedConsumerWarps * 32;
+
+struct FusedParams {
+  int64_t P;
+  int I;
+  int R;        // rows per stage (multiple of 16)
+  int nstage;   // ring depth
+  int form;     // VIBO_ELBO_*
+  int missing_policy;
+  float beta;
+  const float* resp;
+  const uint8_t* mask;
+  const float* eps;        // (P, D)
+  const float* item_feat;  // (I, F)
+  const float* table;      // (2, 1, 2D)
+  float* out_mu;           // (P, D) or null
+  float* out_lv;
+  float* out_theta;
+  double* part_scalar;     // [grid][2]
+  float* part_table;       // [grid][4D]  (A0 | A1 | B0 | B1)
+  float* part_item;        // [grid][I*F]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completing `bytes` on `bar`.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__host__ __device__ inline size_t fused_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Shared-memory layout (bytes): barriers | item params (SoA floats) | stages.
+struct FusedSmem {
+  size_t params_off, stage_off, stage_bytes, resp_bytes, mask_off, eps_off, total;
+};
+__host__ __device__ inline FusedSmem fused_smem_layout(int I, int D, int model, int R, int nstage) {
+  FusedSmem L;
+  const int nparam = model == 1 ? 1 : (model == 2 ? D + 1 : D + 2);
+  L.params_off = 128;
+  L.stage_off = fused_align(L.params_off + (size_t)nparam * I * 4, 128);
+  L.resp_bytes = (size_t)R * I * 4;
+  L.mask_off = L.resp_bytes;
+  L.eps_off = fused_align(L.mask_off + (size_t)R * I, 16);
+  L.stage_bytes = fused_align(L.eps_off + (size_t)R * D * 4, 128);
+  L.total = L.stage_off + (size_t)nstage * L.stage_bytes;
+  return L;
+}
+
+// Fill stage memory `st` with chunk c (rows [c*R, c*R + rows)) and make
+// `bar` complete when the data has landed.  Called by one whole warp.
+template <int D>
+__device__ __forceinline__ void fused_issue_chunk(const FusedParams& p, const FusedSmem& L, int64_t c,
+                                                  unsigned char* st, uint64_t* bar, int lane) {
+  const int I = p.I, R = p.R;
+  const int64_t row0 = c * R;
+  const int rows = (int)((p.P - row0 < R) ? p.P - row0 : R);
+  const uint32_t b_resp = (uint32_t)rows * I * 4, b_mask = (uint32_t)rows * I, b_eps = (uint32_t)rows * D * 4;
+  if (((b_mask | b_eps) & 15u) == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar, b_resp + b_mask + b_eps);
+      bulk_g2s(st, p.resp + row0 * I, b_resp, bar);
+      bulk_g2s(st + L.mask_off, p.mask + row0 * I, b_mask, bar);
+      bulk_g2s(st + L.eps_off, p.eps + row0 * D, b_eps, bar);
+    }
+  } else {
+    // ragged tail chunk: sizes are not 16-byte multiples, copy by hand
+    const float* gr = p.resp + row0 * I;
+    float* sr = reinterpret_cast<float*>(st);
+    for (int k = lane; k < rows * I; k += 32) sr[k] = gr[k];
+    const uint8_t* gm = p.mask + row0 * I;
+    uint8_t* sm = st + L.mask_off;
+    for (int k = lane; k < rows * I; k += 32) sm[k] = gm[k];
+    const float* ge = p.eps + row0 * D;
+    float* se = reinterpret_cast<float*>(st + L.eps_off);
+    for (int k = lane; k < rows * D; k += 32) se[k] = ge[k];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  }
+}
+
+// Pass 2 over one person's row: link, Bernoulli log-likelihood and (GRAD) the
+// per-cell gradient terms.  FULL: every cell of the row is observed, so the
+// mask is not consulted and the 0/1 response bits drive a sign flip directly.
+//   accM += max(-t, 0), accL += log2(1 + 2^(-|t| log2 e))   => ll = -(accM + ln2 accL)
+template <int MODEL, int D, int LPP, int NG, bool GRAD, bool FULL>
+__device__ __forceinline__ void fused_pass2(const float* __restrict__ xr, const uint8_t* __restrict__ mr,
+                                            const float* __restrict__ s_param, int I, int n_groups, int q,
+                                            const float (&th)[D], float tsum, float (&gth)[D],
+                                            float (&acc)[GRAD ? NG * 4 * item_width(MODEL, D) : 1],
+                                            float& accM, float& accL, float& ll3) {
+  constexpr int F = item_width(MODEL, D);
+  constexpr int DA = MODEL == 1 ? 0 : D;
+  constexpr float kNegLog2e = -1.4426950408889634f;
+  const float* s_b = s_param + (size_t)DA * I;
+  const float* s_g = s_param + (size_t)(DA + 1) * I;
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const int g = q + LPP * k;
+    if (g < n_groups) {
+      const float4 x4 = *reinterpret_cast<const float4*>(xr + 4 * g);
+      uint32_t m4 = 0x01010101u;
+      if (!FULL) m4 = *reinterpret_cast<const uint32_t*>(mr + 4 * g);
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b + 4 * g);
+      float4 a4[DA > 0 ? DA : 1];
+#pragma unroll
+      for (int d = 0; d < DA; ++d) a4[d] = *reinterpret_cast<const float4*>(s_param + (size_t)d * I + 4 * g);
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODEL == 3) g4 = *reinterpret_cast<const float4*>(s_g + 4 * g);
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+      const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int cidx = 0; cidx < 4; ++cidx) {
+        float av[DA > 0 ? DA : 1];
+#pragma unroll
+        for (int d = 0; d < DA; ++d)
+          av[d] = cidx == 0 ? a4[d].x : (cidx == 1 ? a4[d].y : (cidx == 2 ? a4[d].z : a4[d].w));
+        float z = bs[cidx];
+        if (MODEL == 1) {
+          z += tsum;
+        } else {
+#pragma unroll
+          for (int d = 0; d < DA; ++d) z = fmaf(-th[d], av[d], z);
+        }
+        const bool o = FULL ? true : ((m4 >> (8 * cidx)) & 0xffu) != 0;
+        float dz = 0.0f, dgam = 0.0f;
+        if (MODEL == 3) {
+          const CellGrad cg = cell_3pl<false>(z, gs[cidx], xs[cidx] > 0.5f);
+          ll3 += o ? cg.ll : 0.0f;
+          dz = o ? cg.dz : 0.0f;
+          dgam = o ? cg.dgam : 0.0f;
+        } else {
+          // u = (2x - 1) z : FULL uses the exponent bit of the 0/1 float
+          uint32_t flip = 0;
+          bool x1 = true;
+          float u;
+          if (FULL) {
+            flip = (~(__float_as_uint(xs[cidx]) << 2)) & 0x80000000u;  // 0 if x == 1, sign bit if x == 0
+            u = __uint_as_float(__float_as_uint(z) ^ flip);
+          } else {
+            x1 = xs[cidx] > 0.5f;
+            u = x1 ? z : -z;
+          }
+          const float t = fminf(fmaxf(u, -kLogitClamp), kLogitClamp);
+          const float e = ex2_approx(fabsf(t) * kNegLog2e);
+          const float w = 1.0f + e;
+          const float lw = lg2_approx(w);
+          if (FULL) {
+            accM += fmaxf(-t, 0.0f);
+            accL += lw;
+          } else {
+            accM += o ? fmaxf(-t, 0.0f) : 0.0f;
+            accL += o ? lw : 0.0f;
+          }
+          if (GRAD) {
+            const float sig = (t >= 0.0f ? e : 1.0f) * rcp_approx(w);  // sigmoid(-t)
+            const float du = (t == u && o) ? sig : 0.0f;               // zero outside the eps32 clamp
+            dz = FULL ? __uint_as_float(__float_as_uint(du) ^ flip) : (x1 ? du : -du);
+          }
+        }
+        if (GRAD) {
+          const int slot = (k * 4 + cidx) * F;
+          if (MODEL == 1) {
+            gth[0] -= dz;  // d loss_k / d theta_d = -sum_j dz (same for every d)
+            acc[slot] += dz;
+          } else {
+#pragma unroll
+            for (int d = 0; d < DA; ++d) {
+              gth[d] = fmaf(dz, av[d], gth[d]);
+              acc[slot + d] = fmaf(dz, th[d], acc[slot + d]);
+            }
+            acc[slot + D] += dz;
+            if (MODEL == 3) acc[slot + D + 1] += dgam;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int MODEL, int D, int LPP, int NG, bool GRAD>
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __grid_constant__ FusedParams p) {
+  constexpr int F = item_width(MODEL, D);
+  constexpr int DA = MODEL == 1 ? 0 : D;  // discrimination arrays
+  (void)DA;
+  constexpr int NW = kFusedConsumerWarps;
+  constexpr int PPW = 32 / LPP;           // persons per warp at a time
+  constexpr int IPL = NG * 4;             // items per lane
+  constexpr float kLn2 = 0.6931471805599453f;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int I = p.I, R = p.R, NS = p.nstage;
+  const FusedSmem L = fused_smem_layout(I, D, MODEL, R, NS);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  int* done_cnt = reinterpret_cast<int*>(full_bar + 8);  // warps finished with each stage
+  float* s_param = reinterpret_cast<float*>(smem + L.params_off);  // [a_0 | .. | a_{D-1} | b | guess]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_groups = I >> 2;
+  const int64_t n_chunks = (p.P + R - 1) / R;
+
+  // ---- one-time setup ----------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      done_cnt[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < I; j += blockDim.x) {
+    if (MODEL == 1) {
+      s_param[j] = p.item_feat[j];
+    } else {
+      for (int d = 0; d < D; ++d) s_param[(size_t)d * I + j] = p.item_feat[(size_t)j * F + d];
+      s_param[(size_t)D * I + j] = p.item_feat[(size_t)j * F + D];
+      if (MODEL == 3)
+        s_param[(size_t)(D + 1) * I + j] = 1.0f / (1.0f + expf(-p.item_feat[(size_t)j * F + D + 1]));
+    }
+  }
+  __syncthreads();
+
+  // per-CTA results
+  double ll_acc = 0.0, term_acc = 0.0;
+  float tA[2][D], tB[2][D];
+  float acc[GRAD ? IPL * F : 1];
+#pragma unroll
+  for (int d = 0; d < D; ++d) tA[0][d] = tA[1][d] = tB[0][d] = tB[1][d] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < (GRAD ? IPL * F : 1); ++k) acc[k] = 0.0f;
+
+  // prologue: the first NS chunks of this CTA
+  if (warp == 0) {
+    for (int s = 0; s < NS; ++s) {
+      const int64_t c = blockIdx.x + (int64_t)s * gridDim.x;
+      if (c < n_chunks)
+        fused_issue_chunk<D>(p, L, c, smem + L.stage_off + (size_t)s * L.stage_bytes, &full_bar[s], lane);
+    }
+  }
+  {
+    // ======================= consumer warps ==============================
+    const int sub = lane / LPP, q = lane % LPP;
+    // expert table -> precisions (utils.py:107-108); same for every person
+    float tau[2][D], mt[2][D];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float mu = p.table[r * 2 * D + d], lam = p.table[r * 2 * D + D + d];
+        tau[r][d] = 1.0f / (expf(lam) + kPoeEps);
+        mt[r][d] = mu * tau[r][d];
+      }
+    const float prior_tau = p.missing_policy == VIBO_MISSING_PRIOR ? 1.0f / (1.0f + kPoeEps) : 0.0f;
+
+    int it = 0;
+    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+      const int s = it % NS;
+      mbar_wait(&full_bar[s], (it / NS) & 1);
+      const unsigned char* st = smem + L.stage_off + (size_t)s * L.stage_bytes;
+      const int64_t row0 = c * R;
+      const int rows = (int)((p.P - row0 < R) ? p.P - row0 : R);
+      for (int rbase = warp * PPW; rbase < rows; rbase += NW * PPW) {
+        const int r = rbase + sub;
+        const bool valid = r < rows;
+        const int rr = valid ? r : rbase;  // keep addresses in range for idle sub-groups
+        const float* xr = reinterpret_cast<const float*>(st) + (size_t)rr * I;
+        const uint8_t* mr = st + L.mask_off + (size_t)rr * I;
+        const float* er = reinterpret_cast<const float*>(st + L.eps_off) + (size_t)rr * D;
+
+        // ---- pass 1: counts ------------------------------------------------
+        float n1f = 0.0f;
+        uint32_t mand = 0x01010101u;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+          const int g = q + LPP * k;
+          if (g < n_groups) {
+            const float4 x = *reinterpret_cast<const float4*>(xr + 4 * g);
+            const uint32_t m = *reinterpret_cast<const uint32_t*>(mr + 4 * g);
+            n1f += (x.x + x.y) + (x.z + x.w);
+            mand &= m;
+          }
+        }
+        const bool full_obs = __all_sync(0xffffffffu, mand == 0x01010101u);
+        float nobsf = (float)I;
+        if (!full_obs) {
+          int n1 = 0, nobs = 0;
+#pragma unroll
+          for (int k = 0; k < NG; ++k) {
+            const int g = q + LPP * k;
+            if (g < n_groups) {
+              const float4 x = *reinterpret_cast<const float4*>(xr + 4 * g);
+              const uint32_t m = *reinterpret_cast<const uint32_t*>(mr + 4 * g);
+              const bool o0 = (m & 0xffu) != 0, o1 = (m & 0xff00u) != 0, o2 = (m & 0xff0000u) != 0,
+                         o3 = (m & 0xff000000u) != 0;
+              nobs += (int)o0 + (int)o1 + (int)o2 + (int)o3;
+              n1 += (int)(o0 && x.x > 0.5f) + (int)(o1 && x.y > 0.5f) + (int)(o2 && x.z > 0.5f) +
+                    (int)(o3 && x.w > 0.5f);
+            }
+          }
+          n1f = (float)n1;
+          nobsf = (float)nobs;
+        }
+#pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) {
+          n1f += __shfl_xor_sync(0xffffffffu, n1f, o);
+          if (!full_obs) nobsf += __shfl_xor_sync(0xffffffffu, nobsf, o);
+        }
+        const float n0f = nobsf - n1f, nmiss = (float)I - nobsf;
+
+        // ---- per-person posterior and draw ---------------------------------
+        float amu[D], Ssum[D], sd[D], th[D], epsv[D], alv[D];
+        float tsum = 0.0f;
+        float term = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float S = fmaf(n0f, tau[0][d], fmaf(n1f, tau[1][d], nmiss * prior_tau));
+          const float N = fmaf(n0f, mt[0][d], n1f * mt[1][d]);
+          const float invS = __fdividef(1.0f, S);  // = exp(logvar)
+          Ssum[d] = invS;
+          amu[d] = N * invS;
+          alv[d] = -kLn2 * lg2_approx(S);          // log(1 / S)
+          sd[d] = rsqrtf(S);                       // exp(logvar / 2)
+          epsv[d] = er[d];
+          th[d] = fmaf(epsv[d], sd[d], amu[d]);
+          tsum += th[d];
+          if (p.form == VIBO_ELBO_KL) {
+            term += -0.5f * (1.0f + alv[d] - amu[d] * amu[d] - invS);
+          } else {
+            // log p(theta) - log q(theta); theta - mu = sd * eps exactly
+            term += -0.5f * th[d] * th[d] + 0.5f * epsv[d] * epsv[d] + 0.5f * alv[d];
+          }
+        }
+        if (valid && q == 0) {
+          term_acc += (double)term;
+          const int64_t row = row0 + r;
+          if (p.out_mu != nullptr) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              p.out_mu[row * D + d] = amu[d];
+              p.out_lv[row * D + d] = alv[d];
+              p.out_theta[row * D + d] = th[d];
+            }
+          }
+        }
+
+        // ---- pass 2: link, log-likelihood, gradients -----------------------
+        float gth[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) gth[d] = 0.0f;
+        float accM = 0.0f, accL = 0.0f, ll3 = 0.0f;
+        if (!valid) {
+          // idle sub-group of a ragged tail: contributes nothing (its lanes
+          // still take part in the shuffles below)
+        } else if (full_obs)
+          fused_pass2<MODEL, D, LPP, NG, GRAD, true>(xr, mr, s_param, I, n_groups, q, th, tsum, gth, acc, accM, accL, ll3);
+        else
+          fused_pass2<MODEL, D, LPP, NG, GRAD, false>(xr, mr, s_param, I, n_groups, q, th, tsum, gth, acc, accM, accL, ll3);
+        if (valid) ll_acc += (double)(MODEL == 3 ? ll3 : -(accM + kLn2 * accL));
+
+        // ---- per-person backward -------------------------------------------
+        if (GRAD) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            float gv = MODEL == 1 ? gth[0] : gth[d];
+#pragma unroll
+            for (int o = LPP / 2; o > 0; o >>= 1) gv += __shfl_xor_sync(0xffffffffu, gv, o);
+            float g_mu, g_lv;
+            if (p.form == VIBO_ELBO_KL) {
+              g_mu = fmaf(p.beta, amu[d], gv);
+              g_lv = 0.5f * gv * epsv[d] * sd[d] + 0.5f * p.beta * (Ssum[d] - 1.0f);
+            } else {
+              gv += th[d];
+              g_mu = gv;
+              g_lv = 0.5f * gv * epsv[d] * sd[d] - 0.5f;
+            }
+            const float GN = g_mu * Ssum[d];  // Ssum holds 1 / S
+            const float GS = -(g_mu * amu[d] + g_lv) * Ssum[d];
+            if (valid && q == 0) {
+              tA[0][d] = fmaf(n0f, GN, tA[0][d]);
+              tA[1][d] = fmaf(n1f, GN, tA[1][d]);
+              tB[0][d] = fmaf(n0f, GS, tB[0][d]);
+              tB[1][d] = fmaf(n1f, GS, tB[1][d]);
+            }
+          }
+        }
+      }
+      // the last warp to leave the stage refills it with the chunk NS iterations ahead
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        last = atomicAdd(&done_cnt[s], 1) == NW - 1;
+        if (last) atomicExch(&done_cnt[s], 0);
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        const int64_t cn = c + (int64_t)NS * gridDim.x;
+        if (cn < n_chunks)
+          fused_issue_chunk<D>(p, L, cn, smem + L.stage_off + (size_t)s * L.stage_bytes, &full_bar[s], lane);
+      }
+    }
+  }
+
+  // ---- CTA-level combine (deterministic order) -----------------------------
+  __syncthreads();  // every stage consumed; stage memory is free for reuse
+  double* s_d = reinterpret_cast<double*>(smem + L.stage_off);          // [NW+1][2]
+  float* s_t = reinterpret_cast<float*>(smem + L.stage_off + 1024);     // [NW+1][4D]
+  float* s_item = reinterpret_cast<float*>(smem + L.stage_off + 4096);  // [I*F]
+  {
+    const double a = warp_sum(ll_acc), b = warp_sum(term_acc);
+    if (lane == 0) {
+      s_d[warp * 2] = a;
+      s_d[warp * 2 + 1] = b;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float v0 = warp_sum(tA[0][d]), v1 = warp_sum(tA[1][d]), v2 = warp_sum(tB[0][d]),
+                  v3 = warp_sum(tB[1][d]);
+      if (lane == 0) {
+        s_t[warp * 4 * D + d] = v0;
+        s_t[warp * 4 * D + D + d] = v1;
+        s_t[warp * 4 * D + 2 * D + d] = v2;
+        s_t[warp * 4 * D + 3 * D + d] = v3;
+      }
+    }
+  }
+  if (GRAD) {
+    for (int k = threadIdx.x; k < I * F; k += blockDim.x) s_item[k] = 0.0f;
+    // fold the PPW sub-groups of a warp (same items, different persons)
+#pragma unroll
+    for (int k = 0; k < IPL * F; ++k) {
+#pragma unroll
+      for (int o = LPP; o < 32; o <<= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+  }
+  __syncthreads();
+  if (GRAD) {
+    for (int w = 0; w < NW; ++w) {
+      if (warp == w && lane < LPP) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+          const int g = lane + LPP * k;
+          if (g < n_groups) {
+#pragma unroll
+            for (int cidx = 0; cidx < 4; ++cidx)
+#pragma unroll
+              for (int f = 0; f < F; ++f) s_item[(size_t)(4 * g + cidx) * F + f] += acc[(k * 4 + cidx) * F + f];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    float* dst = p.part_item + (size_t)blockIdx.x * I * F;
+    for (int k = threadIdx.x; k < I * F; k += blockDim.x) dst[k] = s_item[k];
+  }
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < NW; ++w) {
+      a += s_d[w * 2];
+      b += s_d[w * 2 + 1];
+    }
+    p.part_scalar[(size_t)blockIdx.x * 2] = a;
+    p.part_scalar[(size_t)blockIdx.x * 2 + 1] = b;
+  }
+  if (GRAD && threadIdx.x < 4 * D) {
+    float v = 0.0f;
+    for (int w = 0; w < NW; ++w) v += s_t[w * 4 * D + threadIdx.x];
+    p.part_table[(size_t)blockIdx.x * 4 * D + threadIdx.x] = v;
+  }
+}
+
+// Launcher for one (MODEL, D); picks LPP / NG from I.  Defined per
+// instantiation file so the variants compile in parallel.
+template <int MODEL, int D>
+cudaError_t launch_fused_md(const FusedParams& p, int grid, size_t smem, bool grad, cudaStream_t st);
+
+template <int MODEL, int D, int LPP, int NG>
+static cudaError_t launch_fused_cfg(const FusedParams& p, int grid, size_t smem, bool grad, cudaStream_t st) {
+  cudaError_t e;
+  if (grad) {
+    auto k = fused_uncond_kernel<MODEL, D, LPP, NG, true>;
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<grid, kFusedThreads, smem, st>>>(p);
+  } else {
+    auto k = fused_uncond_kernel<MODEL, D, LPP, NG, false>;
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    k<<<grid, kFusedThreads, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+// lanes per person and 4-item groups per lane for I items (I % 4 == 0, I <= 1024)
+inline void fused_pick(int I, int* lpp, int* ng) {
+  const int groups = I / 4;
+  int l = groups <= 8 * 8 ? 8 : (groups <= 16 * 8 ? 16 : 32);
+  int per = (groups + l - 1) / l;
+  *lpp = l;
+  *ng = per <= 4 ? 4 : 8;
+}
+
+#define VIBO_FUSED_INSTANTIATE(MODEL, D)                                                              \
+  template <>                                                                                         \
+  cudaError_t launch_fused_md<MODEL, D>(const FusedParams& p, int grid, size_t smem, bool grad,       \
+                                        cudaStream_t st) {                                            \
+    int lpp, ng;                                                                                      \
+    fused_pick(p.I, &lpp, &ng);                                                                       \
+    if (lpp == 8 && ng == 4) return launch_fused_cfg<MODEL, D, 8, 4>(p, grid, smem, grad, st);        \
+    if (lpp == 8 && ng == 8) return launch_fused_cfg<MODEL, D, 8, 8>(p, grid, smem, grad, st);        \
+    if (lpp == 16 && ng == 4) return launch_fused_cfg<MODEL, D, 16, 4>(p, grid, smem, grad, st);      \
+    if (lpp == 16 && ng == 8) return launch_fused_cfg<MODEL, D, 16, 8>(p, grid, smem, grad, st);      \
+    if (lpp == 32 && ng == 4) return launch_fused_cfg<MODEL, D, 32, 4>(p, grid, smem, grad, st);      \
+    return launch_fused_cfg<MODEL, D, 32, 8>(p, grid, smem, grad, st);                                \
+  }
+
+}  // namespace vibo
