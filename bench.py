@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the VIBO ELBO hot path (BASELINE.json metric: ELBO evals/sec,
+reported as person x item cells/s, 2PL synthetic).
+
+    python bench.py --gpus N --steps K --warmup W            # native arm
+    python bench.py --impl reference --steps K --warmup W    # reference CPU arm
+
+One "step" is one pass of the hot path over the whole resident response
+matrix: by default a full training step (zero_grad, fused forward+backward of
+the ELBO, [all-reduce of the loss and parameter gradients at N > 1], Adam) --
+the body of the reference's vibo.py:243-268 -- with the matrix as one batch;
+``--mode eval`` times the forward-only ELBO evaluation instead.
+
+Workload (``--workload``): c4 (default) = 2PL, 1,000,000 x 1,000, ability-dim
+1 -- the configuration BASELINE.json's north-star roofline target is quoted on
+(it fits one GPU: 5 GB at 5 B/cell).  At N GPUs every rank holds one such shard
+(weak scaling; persons shard with no data-path collective; one NCCL all-reduce
+of [loss, gradients] per step).  Rows are much larger than L2 (126 MB), so no
+L2 flush is needed between timed iterations.
+
+Rank 0 prints ONE JSON line (see the task contract for the keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (irt_model, P, I, D, conditional, missing_frac, n_flows)
+    "c1": (2, 8000, 100, 1, False, 0.0, 0),          # train split of 10000 x 100
+    "c2": (2, 100000, 500, 1, False, 0.0, 0),
+    "c3": (3, 1000000, 1000, 5, True, 0.0, 0),
+    "c4": (2, 1000000, 1000, 1, False, 0.0, 0),
+    "c4shard": (2, 125000, 1000, 1, False, 0.0, 0),  # one rank's share of c4 at 8 GPUs
+    "c5": (2, 428478, 95, 1, False, 0.1, 2),
+    "tiny": (2, 4096, 100, 1, False, 0.0, 0),
+}
+BYTES_PER_CELL = 5  # float32 response + uint8 mask
+
+
+def describe(name):
+    irt, P, I, D, cond, miss, flows = WORKLOADS[name]
+    s = f"{irt}PL synthetic {P}x{I} ability-dim {D}"
+    if cond:
+        s += " conditional-posterior"
+    if miss:
+        s += f" {int(miss * 100)}% missing"
+    if flows:
+        s += f" {flows} planar flows"
+    return s
+
+
+def synth_rows(P, I, D, irt, miss, device, seed=42):
+    """Plain-torch restatement of the reference's simulator
+    (src/pyro_core/models.py:68-110 via src/simulate.py): abilities, item
+    features, Bernoulli responses; generated on `device` in person blocks."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    F = {1: 1, 2: D + 1, 3: D + 2}[irt]
+    item = torch.randn(I, F, generator=g, device=device)
+    resp = torch.empty(P, I, dtype=torch.float32, device=device)
+    mask = torch.ones(P, I, dtype=torch.bool, device=device)
+    blk = 65536
+    for a in range(0, P, blk):
+        b = min(P, a + blk)
+        ability = torch.randn(b - a, D, generator=g, device=device)
+        if irt == 1:
+            z = ability.sum(1, keepdim=True) + item[:, 0][None, :]
+        else:
+            z = ability @ (-item[:, :D].T) + item[:, D][None, :]
+        p = torch.sigmoid(z)
+        if irt == 3:
+            gs = torch.sigmoid(item[:, D + 1])[None, :]
+            p = gs + (1 - gs) * p
+        resp[a:b] = torch.bernoulli(p, generator=g)
+        if miss > 0:
+            m = torch.rand(b - a, I, generator=g, device=device) >= miss
+            mask[a:b] = m
+            resp[a:b][~m] = -1.0
+    return resp.unsqueeze(2), mask.unsqueeze(2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [l.split(", ") for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or \
+               [l.split(", ") for (_, l) in self.lines[-3:]]
+        sm, reasons, smax = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the fused kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_kernel_ncu.json")) as f:
+            rec = json.load(f)
+        if rec.get("workload") == workload:
+            return rec.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
+# --------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# --------------------------------------------------------------------------
+def run_reference_cpu(workload, steps, warmup, mode, sample_persons=None, batch=256):
+    """Times the reference's own CPU implementation of the step -- per-cell
+    encoder MLP over (B*I, 1) rows, PoE, torch.mm link, Bernoulli.log_prob,
+    autograd backward, Adam: oracle/reference_port.py restates
+    src/torch_core/models.py + vibo.py:243-268 op for op (/root/reference is
+    not present on the GPU box, so the port stands in: kind "port")."""
+    import torch
+    from oracle import reference_port as RP
+    irt, P, I, D, cond, miss, flows = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if sample_persons is None:
+        # sized for ~2 s per step at the ~2 Mcells/s the reference reaches
+        sample_persons = max(batch, min(P, (4_000_000 // I) // batch * batch))
+    resp, mask = synth_rows(sample_persons, I, D, irt, miss, "cpu")
+    mask_l = mask.long()
+    torch.manual_seed(42)
+    params = RP.init_params(irt, D, I, conditional=cond, n_flows=flows)
+    state = {}
+    F = RP.item_feat_width(irt, D)
+    kw = dict(irt_model=irt, ability_dim=D, conditional=cond, n_flows=flows,
+              use_kl_divergence=(flows == 0))
+
+    def one_step():
+        for a in range(0, sample_persons, batch):
+            r, m = resp[a:a + batch], mask_l[a:a + batch]
+            e_i = torch.randn(I, F)
+            e_a = torch.randn(r.shape[0], D)
+            if mode == "train":
+                RP.adam_train_step(params, state, r, m, e_i, e_a, **kw)
+            else:
+                RP.loss_and_grads(params, r, m, e_i, e_a, want_grads=False, **kw)
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    cells = sample_persons * I * steps
+    return {"value": cells / dt, "ms_per_step": dt / steps * 1e3, "cores": cores,
+            "sample": f"{sample_persons} persons x {I} items in minibatches of {batch} "
+                      f"({mode} step, fp32, {torch.get_num_threads()} torch threads)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="capture the step in a CUDA graph (1/0)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    irt, P, I, D, cond, miss, flows = WORKLOADS[args.workload]
+    metric = "ELBO evals/sec (person x item cells/s)"
+
+    # ------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 10))
+        r = run_reference_cpu(args.workload, steps, max(1, min(args.warmup, 2)), args.mode)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "cells/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": describe(args.workload), "mode": args.mode,
+                           "note": "CPU; each step is a bounded sample of the workload"},
+                "cpu_baseline": {"value": r["value"], "unit": "cells/s", "cores": r["cores"],
+                                 "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "cells/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # --------------------------------------------------------------- native arm
+    import torch
+    import torch.distributed as dist
+    import vibo_b200
+    from vibo_b200 import distributed as vdist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = vibo_b200._lib.load()
+
+    resp, mask = synth_rows(P, I, D, irt, miss, dev, seed=42 + rank)
+    torch.manual_seed(42)
+    cls = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[irt]
+    model = cls(D, I, hidden_dim=64, ability_merge="product", conditional_posterior=cond,
+                n_norm_flows=flows).to(dev)
+    trainer = vdist.ShardedElboTrainer(model, lr=5e-3, world_size=world, rank=rank,
+                                       person_offset=rank * P, use_kl_divergence=(flows == 0),
+                                       cuda_graph=bool(args.cuda_graph))
+
+    def step(i):
+        if args.mode == "train":
+            return trainer.train_step(resp, mask, step_index=i)
+        return trainer.eval_step(resp, mask, step_index=i)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.vibo_launch_count()
+    lib.vibo_profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        out = step(args.warmup + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    import ctypes
+    n_l, tot_ms = ctypes.c_int(0), ctypes.c_double(0.0)
+    lib.vibo_profile_end(ctypes.byref(n_l), ctypes.byref(tot_ms))
+    launches = int(lib.vibo_launch_count() - launches0)
+    if trainer.graph_replays:
+        launches = trainer.kernels_per_step * args.steps
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    loss_val = float(out.item()) if out is not None else None
+
+    cells_per_step = P * I * world
+    value = cells_per_step * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel: device time of the fused kernel alone,
+    # bracketed by CUDA events on its launch stream (vibo_profile_*); when the
+    # step is replayed from a CUDA graph the brackets are taken on a separate
+    # un-graphed timing pass of the same step.
+    if n_l.value == 0:
+        lib.vibo_profile_begin()
+        for i in range(5):
+            trainer.train_step(resp, mask, step_index=1000 + i, force_eager=True) if args.mode == "train" \
+                else trainer.eval_step(resp, mask, step_index=1000 + i, force_eager=True)
+        torch.cuda.synchronize()
+        lib.vibo_profile_end(ctypes.byref(n_l), ctypes.byref(tot_ms))
+    peak, peak_src = measured_peak()
+    roofline = None
+    if n_l.value > 0:
+        k_ms = tot_ms.value / n_l.value
+        achieved = P * I * BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                    "kernel": "fused_uncond_kernel" if trainer.uses_fused else "general kernels",
+                    "kernel_ms": k_ms, "algorithmic_bytes_per_cell": BYTES_PER_CELL,
+                    "peak_source": peak_src}
+
+    # end-to-end through the public API with HOST (pinned) rows: H2D of the
+    # step's rows and D2H of the loss inside the timed region.
+    e2e = None
+    if not args.no_e2e and flows == 0:
+        Pe = min(P, 262144) if args.workload == "c4" and os.environ.get("VIBO_E2E_FULL") != "1" else P
+        resp_h = resp[:Pe].cpu().pin_memory()
+        mask_h = mask[:Pe].cpu().pin_memory()
+        for i in range(2):
+            trainer.train_step(resp_h, mask_h, step_index=i) if args.mode == "train" else \
+                trainer.eval_step(resp_h, mask_h, step_index=i)
+        torch.cuda.synchronize()
+        ksteps = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(ksteps):
+            o = trainer.train_step(resp_h, mask_h, step_index=i) if args.mode == "train" else \
+                trainer.eval_step(resp_h, mask_h, step_index=i)
+            _ = o.item()
+        e1.record()
+        torch.cuda.synchronize()
+        ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": Pe * I * world * ksteps / (float(ems.item()) * 1e-3), "unit": "cells/s",
+               "h2d_bytes_per_step": Pe * I * BYTES_PER_CELL, "d2h_bytes_per_step": 16,
+               "rows_per_step": Pe, "steps": ksteps,
+               "note": "pinned host response/mask -> vibo_fused_elbo_host (chunked H2D overlapped "
+                       "with the kernel) -> loss read back"}
+        del resp_h, mask_h
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_reference_cpu(args.workload, 3, 1, args.mode)
+        cpu_baseline = {"value": r["value"], "unit": "cells/s", "cores": r["cores"], "kind": "port",
+                        "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "cells/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": describe(args.workload), "mode": args.mode,
+                           "rows_per_gpu": P, "items": I,
+                           "l2": "inputs (%.2f GB/GPU) >> 126 MB L2, no flush" % (P * I * 5 / 1e9)
+                           if P * I * 5 > 4 * 126e6 else "inputs fit L2; no flush (small parity config)",
+                           "parallelism": f"person-sharded dp{world}",
+                           "cuda_graph": bool(trainer.graph_replays)},
+                "evals_per_sec": args.steps / (total_ms * 1e-3), "loss": loss_val,
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "e2e": e2e, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,23 @@ int vibo_bernoulli_loglik(const vibo_desc* desc, const float* response, const ui
                           const float* response_mu, double* out_ll, float* g_prob,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Measurement hooks (used by bench.py; no effect on results).
+ *   vibo_launch_count      kernels this library has launched in this process.
+ *   vibo_profile_begin     start bracketing every launch of the fused kernel
+ *                          with CUDA events on the launching stream.
+ *   vibo_profile_end       stop; synchronises the recorded events and returns
+ *                          the number of bracketed launches and their total
+ *                          device time in milliseconds.
+ *   vibo_single_pass       1 if vibo_fused_elbo would run the single-pass
+ *                          kernel for `desc` (16-byte aligned rows assumed),
+ *                          0 if it composes the general kernels.
+ */
+int vibo_single_pass(const vibo_desc* desc);
+uint64_t vibo_launch_count(void);
+int vibo_profile_begin(void);
+int vibo_profile_end(int* n_launches, double* total_ms);
+
 #ifdef __cplusplus
 }
 #endif

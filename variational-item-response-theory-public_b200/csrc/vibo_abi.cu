@@ -91,6 +91,20 @@ extern "C" {
 
 int vibo_version(void) { return VIBO_B200_VERSION; }
 
+int vibo_single_pass(const vibo_desc* desc) {
+  if (check_desc(desc) != VIBO_OK) return 0;
+  return vibo::fused_supported(*desc, nullptr, nullptr) ? 1 : 0;
+}
+
+uint64_t vibo_launch_count(void) { return (uint64_t)vibo::launch_count(); }
+
+int vibo_profile_begin(void) {
+  vibo::profile_begin();
+  return VIBO_OK;
+}
+
+int vibo_profile_end(int* n_launches, double* total_ms) { return vibo::profile_end(n_launches, total_ms); }
+
 const char* vibo_last_error(void) { return g_last_error.c_str(); }
 
 size_t vibo_workspace_bytes(const vibo_desc* desc) {

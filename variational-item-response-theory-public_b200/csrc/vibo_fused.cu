@@ -1,8 +1,9 @@
 // Dispatch, workspace carving and finalisation of the single-pass fused ELBO
 // kernel (vibo_fused_kernel.cuh).
 #include <cstdlib>
+#include <vector>
 
-#include "vibo_fused_kernel.cuh"
+#include "vibo_fused2_kernel.cuh"
 
 namespace vibo {
 
@@ -12,9 +13,12 @@ constexpr size_t kSmemBudget = 200 * 1024;  // stages + params; 227 KB is the ha
 
 struct FusedPlan {
   bool ok = false;
+  bool two_phase = false;  // fused2_kernel (1PL / 2PL) vs the register-accumulator kernel
   int R = 0, nstage = 0, grid = 0;
   size_t smem = 0;
 };
+
+constexpr size_t kSmemCap = 227 * 1024;
 
 bool fused_model_dim(int model, int D) {
   return (model == 1 && D == 1) || (model == 2 && D == 1) || (model == 3 && D == 1) || (model == 2 && D == 2);
@@ -26,19 +30,32 @@ FusedPlan fused_plan(const vibo_desc& d) {
   if (d.conditional || (I & 3) != 0 || I > 1024 || I < 4 || !fused_model_dim(d.irt_model, D)) return pl;
   int lpp, ng;
   fused_pick(I, &lpp, &ng);
-  const int r_min = kFusedConsumerWarps * (32 / lpp);  // every consumer warp busy in each stage
+  // rows per stage: a multiple of (a) what one pass of a team covers and (b)
+  // the alignment quantum that keeps every bulk copy a 16-byte multiple at a
+  // 16-byte aligned address (mask rows are I bytes, eps rows 4*D bytes)
+  auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+  const int q_mask = 16 / gcd(I, 16), q_eps = 4 / gcd(D, 4);
+  const bool two_phase = d.irt_model != 3;
+  const int n_teams = two_phase ? kF2Teams : kFusedTeams;
+  const int scratch = two_phase ? kF2ScratchBytes : 0;
+  const int r_pass = (two_phase ? kF2TeamWarps : kFusedTeamWarps) * (32 / lpp);
+  int r_min = r_pass;
+  while (r_min % q_mask != 0 || r_min % q_eps != 0) r_min += r_pass;
   const size_t row_bytes = (size_t)I * 5 + (size_t)D * 4;
   int R = r_min;
-  while ((size_t)(R + r_min) * row_bytes <= 48 * 1024) R += r_min;
+  if (two_phase && r_min > kF2MaxRows) return pl;
+  while ((size_t)(R + r_min) * row_bytes <= 24 * 1024 && (!two_phase || R + r_min <= kF2MaxRows)) R += r_min;
   // small problems: keep enough chunks to spread over the SMs
-  while (R > r_min && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count()) R -= r_min;
-  int ns = 4;
-  FusedSmem L = fused_smem_layout(I, D, d.irt_model, R, ns);
-  while (ns > 2 && L.total > kSmemBudget) {
+  while (R > r_min && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count() * n_teams) R -= r_min;
+  int ns = two_phase ? 3 : 4;  // at most 16 mbarriers per CTA
+  const size_t budget = two_phase ? kSmemCap : kSmemBudget;
+  FusedSmem L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch);
+  while (ns > 2 && L.total > budget) {
     --ns;
-    L = fused_smem_layout(I, D, d.irt_model, R, ns);
+    L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch);
   }
-  if (L.total > kSmemBudget) return pl;
+  if (L.total > budget) return pl;
+  pl.two_phase = two_phase;
   const int F = item_width_host(d.irt_model, D);
   size_t smem = L.total;
   const size_t tail = L.stage_off + 4096 + (size_t)I * F * 4;  // combine scratch reuses the stages
@@ -47,7 +64,8 @@ FusedPlan fused_plan(const vibo_desc& d) {
   pl.R = R;
   pl.nstage = ns;
   pl.smem = smem;
-  pl.grid = (int)(n_chunks < sm_count() ? n_chunks : sm_count());
+  const int64_t want = (n_chunks + n_teams - 1) / n_teams;
+  pl.grid = (int)(want < sm_count() ? want : sm_count());
   if (pl.grid < 1) pl.grid = 1;
   pl.ok = true;
   return pl;
@@ -109,7 +127,36 @@ __global__ void fused_finalize_kernel(int nparts, int I, int F, int DA, int D, b
   }
 }
 
+// ---- measurement hooks (vibo_profile_begin / vibo_profile_end) -------------
+struct EventPair { cudaEvent_t a, b; };
+bool g_profiling = false;
+std::vector<EventPair> g_events;
+
 }  // namespace
+
+void profile_begin() {
+  g_events.clear();
+  g_profiling = true;
+}
+
+int profile_end(int* n, double* total_ms) {
+  g_profiling = false;
+  double tot = 0.0;
+  int cnt = 0;
+  for (auto& ev : g_events) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(ev.b) == cudaSuccess && cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {
+      tot += ms;
+      ++cnt;
+    }
+    cudaEventDestroy(ev.a);
+    cudaEventDestroy(ev.b);
+  }
+  g_events.clear();
+  if (n) *n = cnt;
+  if (total_ms) *total_ms = tot;
+  return 0;
+}
 
 bool fused_supported(const vibo_desc& d, const float* resp, const uint8_t* mask) {
   // VIBO_DISABLE_FUSED=1 routes everything through the composed general
@@ -148,6 +195,7 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
     int64_t blocks = (d.num_person + 255) / 256;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
     philox_fill_kernel<<<(int)blocks, 256, 0, st>>>(d.num_person, D, d.person_offset, seed, eps_buf);
+    note_launch();
     eps = eps_buf;
   } else if (reinterpret_cast<uintptr_t>(eps) & 15) {
     cudaError_t e = cudaMemcpyAsync(eps_buf, eps, (size_t)d.num_person * D * sizeof(float),
@@ -158,18 +206,33 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   const bool grad = g_item != nullptr;
   FusedParams p;
   p.P = d.num_person; p.I = d.num_item; p.R = pl.R; p.nstage = pl.nstage; p.form = d.elbo_form;
-  p.missing_policy = d.missing_policy; p.beta = beta; p.resp = resp; p.mask = mask; p.eps = eps;
+  p.missing_policy = d.missing_policy; p.beta = beta;
+  { const char* dbg = getenv("VIBO_FUSED_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; } p.resp = resp; p.mask = mask; p.eps = eps;
   p.item_feat = item_feat; p.table = table;
   const bool person_out = amu != nullptr && alv != nullptr && ability != nullptr;
   p.out_mu = person_out ? amu : nullptr; p.out_lv = person_out ? alv : nullptr;
   p.out_theta = person_out ? ability : nullptr;
   p.part_scalar = part_scalar; p.part_table = part_table; p.part_item = part_item;
+  EventPair ev{nullptr, nullptr};
+  if (g_profiling) {
+    cudaEventCreate(&ev.a);
+    cudaEventCreate(&ev.b);
+    cudaEventRecord(ev.a, st);
+  }
   cudaError_t e = cudaErrorNotSupported;
-  if (d.irt_model == 1 && D == 1) e = launch_fused_md<1, 1>(p, pl.grid, pl.smem, grad, st);
-  else if (d.irt_model == 2 && D == 1) e = launch_fused_md<2, 1>(p, pl.grid, pl.smem, grad, st);
-  else if (d.irt_model == 3 && D == 1) e = launch_fused_md<3, 1>(p, pl.grid, pl.smem, grad, st);
-  else if (d.irt_model == 2 && D == 2) e = launch_fused_md<2, 2>(p, pl.grid, pl.smem, grad, st);
+  if (pl.two_phase) {
+    if (d.irt_model == 1 && D == 1) e = launch_fused2_md<1, 1>(p, pl.grid, pl.smem, grad, st);
+    else if (d.irt_model == 2 && D == 1) e = launch_fused2_md<2, 1>(p, pl.grid, pl.smem, grad, st);
+    else if (d.irt_model == 2 && D == 2) e = launch_fused2_md<2, 2>(p, pl.grid, pl.smem, grad, st);
+  } else if (d.irt_model == 3 && D == 1) {
+    e = launch_fused_md<3, 1>(p, pl.grid, pl.smem, grad, st);
+  }
+  if (g_profiling) {
+    cudaEventRecord(ev.b, st);
+    g_events.push_back(ev);
+  }
   if (e != cudaSuccess) return e;
+  note_launch(2);
   const int DA = d.irt_model == 1 ? 0 : D;
   const int n = d.num_item * F;
   int fb = (n + 127) / 128;

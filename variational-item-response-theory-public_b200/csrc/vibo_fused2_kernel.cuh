@@ -1,0 +1,532 @@
+// Two-phase single-pass fused ELBO kernel for the unconditional 1PL / 2PL
+// encoder (sm_100a): the production kernel for the headline configuration.
+//
+// Same data movement as vibo_fused_kernel.cuh (per-team rings of 1-D TMA bulk
+// copies on mbarriers; each row read from HBM once).  What differs is where
+// the cross-person item-gradient sums live.  There, each lane keeps the
+// accumulators of the 32 items it owns in registers (64+ registers), which
+// caps the CTA at 16 warps and leaves the kernel latency-bound.  Here a team
+// of 4 warps processes the rows of a stage in two phases:
+//
+//   phase A (one warp per row): counts -> posterior -> draw -> link ->
+//       log-likelihood; d ll / d z of every cell is written back to shared
+//       memory IN PLACE of the response value it was computed from;
+//   team barrier;
+//   phase B (one thread per item group): each of the team's 128 threads owns
+//       one or two 4-item groups for the whole kernel and adds the stage's
+//       rows' d ll / d z (and theta-weighted d ll / d z) into 8..24 registers.
+//
+// Registers drop below 96, so 20 warps (5 teams) are resident per SM.
+//
+// Clamp handling: the eps32 clamp of torch.distributions only acts where
+// |z| > 15.94.  A row whose bound sum_d |theta_d| max_j|a_jd| + max_j|b_j| is
+// below that cannot reach the clamp, and takes a path without the clamp and
+// range-test instructions; other rows take the exact path.
+#pragma once
+
+#include "vibo_fused_kernel.cuh"
+
+namespace vibo {
+
+constexpr int kF2Teams = 5;
+constexpr int kF2TeamWarps = 4;
+constexpr int kF2Warps = kF2Teams * kF2TeamWarps;
+constexpr int kF2Threads = kF2Warps * 32;
+constexpr int kF2TeamThreads = kF2TeamWarps * 32;
+constexpr int kF2GroupsPerThread = 2;     // phase-B groups per thread: I <= 4 * 128 * 2 = 1024
+constexpr int kF2MaxRows = 64;            // rows per stage upper bound (team scratch sizing)
+// scratch between the barrier block and the item parameters:
+//   [0, 64)                  max_j |a_jd| (d < 8), max_j |b_j|
+//   [64, 64 + 5*2048)        per-team theta of the rows of each ring slot:
+//                            [slot < 4][row < 64][d < 2] floats (phase A of the next
+//                            slot may start while a slower warp is still in phase B)
+constexpr int kF2ThetaFloats = 4 * kF2MaxRows * 2;
+constexpr int kF2ScratchBytes = 64 + kF2Teams * kF2ThetaFloats * 4;
+
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void team_barrier(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kF2TeamThreads) : "memory");
+}
+
+// One 4-cell group of phase A.  EXACT keeps the clamp and its range test.
+template <int MODEL, int D, bool GRAD, bool FULL, bool EXACT>
+__device__ __forceinline__ void f2_group(uint32_t xaddr, uint32_t m4, const float4& b4,
+                                         const float4 (&a4)[MODEL == 1 ? 1 : D], const float (&th)[D],
+                                         float tsum, float (&gth)[D], float& s1, float& s2, float& s3) {
+  constexpr int DA = MODEL == 1 ? 0 : D;
+  constexpr float kNegLog2e = -1.4426950408889634f;
+  const float4 x4 = lds128(xaddr);
+  const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+  const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+  float dzs[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float av[DA > 0 ? DA : 1];
+#pragma unroll
+    for (int d = 0; d < DA; ++d) av[d] = c == 0 ? a4[d].x : (c == 1 ? a4[d].y : (c == 2 ? a4[d].z : a4[d].w));
+    float z = bs[c];
+    if (MODEL == 1) {
+      z += tsum;
+    } else {
+#pragma unroll
+      for (int d = 0; d < DA; ++d) z = fmaf(-th[d], av[d], z);
+    }
+    float xm = xs[c] - 0.5f;
+    if (!FULL) {
+      const bool o = ((m4 >> (8 * c)) & 0xffu) != 0;
+      xm = o ? xm : 0.0f;   // missing cell -> neutral cell (x = 1/2, z = 0)
+      z = o ? z : 0.0f;
+    }
+    const float zc = EXACT ? fminf(fmaxf(z, -kLogitClamp), kLogitClamp) : z;
+    const float e = ex2_approx(fabsf(zc) * kNegLog2e);
+    const float w = 1.0f + e;
+    s1 = fmaf(xm, zc, s1);
+    s2 += fabsf(zc);
+    s3 += lg2_approx(w);
+    float dz = 0.0f;
+    if (GRAD) {
+      const float h = rcp_approx(w) - 0.5f;  // sigmoid(|zc|) - 1/2
+      const float cs = __uint_as_float((__float_as_uint(h) & 0x7fffffffu) | (__float_as_uint(zc) & 0x80000000u));
+      dz = xm - cs;                           // x - sigmoid(zc)
+      if (EXACT) dz = (z == zc) ? dz : 0.0f;  // zero gradient outside the eps32 clamp
+      if (MODEL == 1) {
+        gth[0] -= dz;
+      } else {
+#pragma unroll
+        for (int d = 0; d < DA; ++d) gth[d] = fmaf(dz, av[d], gth[d]);
+      }
+    }
+    dzs[c] = dz;
+  }
+  if (GRAD) sts128(xaddr, make_float4(dzs[0], dzs[1], dzs[2], dzs[3]));
+}
+
+template <int MODEL, int D, int LPP, int NG, bool GRAD, bool FULL, bool EXACT>
+__device__ __forceinline__ void f2_pass2(uint32_t xp, uint32_t mp, uint32_t pp, int I4, int kfull, bool has_tail,
+                                         const float (&th)[D], float tsum, float (&gth)[D], float& s1,
+                                         float& s2, float& s3) {
+  constexpr int DA = MODEL == 1 ? 0 : D;
+  float nmiss_lane = 0.0f;
+  auto one = [&](int gi) {
+    uint32_t m4 = 0x01010101u;
+    if (!FULL) {
+      m4 = lds32(mp + gi * 4);
+      nmiss_lane += (float)(4 - __popc(m4 & 0x01010101u));
+    }
+    float4 a4[DA > 0 ? DA : 1];
+#pragma unroll
+    for (int d = 0; d < DA; ++d) a4[d] = lds128(pp + (d * I4 + gi) * 16);
+    const float4 b4 = lds128(pp + (DA * I4 + gi) * 16);
+    f2_group<MODEL, D, GRAD, FULL, EXACT>(xp + gi * 16, m4, b4, a4, th, tsum, gth, s1, s2, s3);
+  };
+#pragma unroll
+  for (int k = 0; k < NG; ++k)
+    if (k < kfull) one(LPP * k);
+  if (has_tail) one(LPP * kfull);
+  if (!FULL) s3 -= nmiss_lane;  // each neutral cell added log2(2) = 1
+}
+
+template <int MODEL, int D, int LPP, int NG, bool GRAD>
+__global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_constant__ FusedParams p) {
+  static_assert(MODEL == 1 || MODEL == 2, "two-phase kernel covers 1PL / 2PL");
+  constexpr int F = item_width(MODEL, D);
+  constexpr int DA = MODEL == 1 ? 0 : D;
+  constexpr int TW = kF2TeamWarps, NQ = kF2Teams;
+  constexpr int PPW = 32 / LPP;
+  constexpr int NGB = kF2GroupsPerThread;
+  constexpr float kLn2 = 0.6931471805599453f;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int I = p.I, R = p.R, NS = p.nstage;
+  const FusedSmem L = fused_smem_layout(I, D, MODEL, R, NS, NQ, kF2ScratchBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);   // [NQ * NS] (<= 16)
+  int* done_cnt = reinterpret_cast<int*>(smem + 128);
+  float* s_max = reinterpret_cast<float*>(smem + 256);      // amax[0..7], bmax
+  float* s_param = reinterpret_cast<float*>(smem + L.params_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = warp / TW, wt = warp % TW, tt = threadIdx.x - team * kF2TeamThreads;
+  const int n_groups = I >> 2;
+  const int64_t n_chunks = (p.P + R - 1) / R;
+  const int64_t chunk0 = (int64_t)blockIdx.x * NQ + team, chunk_step = (int64_t)gridDim.x * NQ;
+  uint64_t* t_full = full_bar + team * NS;
+  int* t_done = done_cnt + team * NS;
+  unsigned char* t_stage = smem + L.stage_off + (size_t)team * NS * L.stage_bytes;
+  static_assert(D <= 2, "theta scratch is sized for D <= 2");
+  float* t_theta = reinterpret_cast<float*>(smem + 256 + 64) + team * kF2ThetaFloats;
+
+  // ---- one-time setup ----------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NQ * NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      done_cnt[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 16) s_max[threadIdx.x] = 0.0f;
+  __syncthreads();
+  {
+    float amax[DA > 0 ? DA : 1], bmax = 0.0f;
+#pragma unroll
+    for (int d = 0; d < (DA > 0 ? DA : 1); ++d) amax[d] = 0.0f;
+    for (int j = threadIdx.x; j < I; j += blockDim.x) {
+      if (MODEL == 1) {
+        const float b = p.item_feat[j];
+        s_param[j] = b;
+        bmax = fmaxf(bmax, fabsf(b));
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float a = p.item_feat[(size_t)j * F + d];
+          s_param[(size_t)d * I + j] = a;
+          amax[d] = fmaxf(amax[d], fabsf(a));
+        }
+        const float b = p.item_feat[(size_t)j * F + D];
+        s_param[(size_t)D * I + j] = b;
+        bmax = fmaxf(bmax, fabsf(b));
+      }
+    }
+    // non-negative floats order like their bit patterns: atomicMax on ints
+#pragma unroll
+    for (int d = 0; d < DA; ++d) atomicMax(reinterpret_cast<int*>(&s_max[d]), __float_as_int(amax[d]));
+    atomicMax(reinterpret_cast<int*>(&s_max[8]), __float_as_int(bmax));
+  }
+  // prologue: the first NS chunks of each team
+  if (wt == 0) {
+    for (int s = 0; s < NS; ++s) {
+      const int64_t c = chunk0 + (int64_t)s * chunk_step;
+      if (c < n_chunks) fused_issue_chunk<D>(p, L, c, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
+    }
+  }
+  __syncthreads();
+
+  // ---- per-thread state ------------------------------------------------------
+  float ll_acc = 0.0f, term_acc = 0.0f;   // per lane; summed in double at the end
+  float tA[2][D], tB[2][D];                // expert-table gradient sums (sub-group leaders)
+  float acc[GRAD ? NGB * 4 * F : 1];       // phase-B item-gradient sums of this thread's groups
+#pragma unroll
+  for (int d = 0; d < D; ++d) tA[0][d] = tA[1][d] = tB[0][d] = tB[1][d] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < (GRAD ? NGB * 4 * F : 1); ++k) acc[k] = 0.0f;
+
+  const int sub = lane / LPP, q = lane % LPP;
+  float tau[2][D], mt[2][D], amaxv[DA > 0 ? DA : 1];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float mu = p.table[r * 2 * D + d], lam = p.table[r * 2 * D + D + d];
+      tau[r][d] = 1.0f / (expf(lam) + kPoeEps);
+      mt[r][d] = mu * tau[r][d];
+    }
+#pragma unroll
+  for (int d = 0; d < DA; ++d) amaxv[d] = s_max[d];
+  const float bmaxv = s_max[8];
+  const float prior_tau = p.missing_policy == VIBO_MISSING_PRIOR ? 1.0f / (1.0f + kPoeEps) : 0.0f;
+  const int kfull = min(n_groups / LPP, NG);
+  const bool has_tail = kfull < NG && q < n_groups - kfull * LPP;
+  uint32_t pp = smem_u32(s_param) + q * 16;
+  asm volatile("mov.u32 %0, %0;" : "+r"(pp));
+
+  const uint32_t stage0 = smem_u32(t_stage), bar0 = smem_u32(t_full), theta0 = smem_u32(t_theta);
+  const int first_row = wt * PPW + sub;
+  const uint32_t off_x = (uint32_t)first_row * I * 4 + q * 16;
+  const uint32_t off_m = (uint32_t)L.mask_off + (uint32_t)first_row * I + q * 4;
+  const uint32_t off_e = (uint32_t)L.eps_off + (uint32_t)first_row * D * 4;
+  const uint32_t step_x = (uint32_t)TW * PPW * I * 4, step_m = (uint32_t)TW * PPW * I,
+                 step_e = (uint32_t)TW * PPW * D * 4;
+  int s = 0;
+  uint32_t phase = 0;
+  int64_t rows_left = p.P - chunk0 * R;
+  const int64_t rows_step = chunk_step * R;
+
+  for (int64_t c = chunk0; c < n_chunks; c += chunk_step, rows_left -= rows_step) {
+    mbar_wait_addr(bar0 + (uint32_t)s * 8, phase);
+    const uint32_t sb = stage0 + (uint32_t)s * (uint32_t)L.stage_bytes;
+    const uint32_t thb = theta0 + (uint32_t)s * (kF2MaxRows * D * 4);  // this slot's theta rows
+    const int rows = rows_left < R ? (int)rows_left : R;
+
+    // ======================= phase A: one sub-group per row =================
+    uint32_t xrow = sb + off_x, mrow = sb + off_m, erow = sb + off_e;
+    for (int rbase = wt * PPW; rbase < rows; rbase += TW * PPW, xrow += step_x, mrow += step_m, erow += step_e) {
+      const int r = rbase + sub;
+      const bool valid = r < rows;
+      const uint32_t xp = valid ? xrow : xrow - (uint32_t)sub * I * 4;
+      const uint32_t mp = valid ? mrow : mrow - (uint32_t)sub * I;
+      const uint32_t ep = valid ? erow : erow - (uint32_t)sub * D * 4;
+
+      // ---- pass 1: counts --------------------------------------------------
+      float n1f = 0.0f;
+      uint32_t mand = 0x01010101u;
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        if (k < kfull) {
+          const float4 x = lds128(xp + LPP * k * 16);
+          n1f += (x.x + x.y) + (x.z + x.w);
+          mand &= lds32(mp + LPP * k * 4);
+        }
+      }
+      if (has_tail) {
+        const float4 x = lds128(xp + LPP * kfull * 16);
+        n1f += (x.x + x.y) + (x.z + x.w);
+        mand &= lds32(mp + LPP * kfull * 4);
+      }
+      const bool full_obs = __all_sync(0xffffffffu, mand == 0x01010101u);
+      float nobsf = (float)I;
+      if (!full_obs) {
+        int n1 = 0, nobs = 0;
+        auto count = [&](int gi) {
+          const float4 x = lds128(xp + gi * 16);
+          const uint32_t m = lds32(mp + gi * 4);
+          const bool o0 = (m & 0xffu) != 0, o1 = (m & 0xff00u) != 0, o2 = (m & 0xff0000u) != 0,
+                     o3 = (m & 0xff000000u) != 0;
+          nobs += (int)o0 + (int)o1 + (int)o2 + (int)o3;
+          n1 += (int)(o0 && x.x > 0.5f) + (int)(o1 && x.y > 0.5f) + (int)(o2 && x.z > 0.5f) +
+                (int)(o3 && x.w > 0.5f);
+        };
+#pragma unroll
+        for (int k = 0; k < NG; ++k)
+          if (k < kfull) count(LPP * k);
+        if (has_tail) count(LPP * kfull);
+        n1f = (float)n1;
+        nobsf = (float)nobs;
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) {
+        n1f += __shfl_xor_sync(0xffffffffu, n1f, o);
+        if (!full_obs) nobsf += __shfl_xor_sync(0xffffffffu, nobsf, o);
+      }
+      const float n0f = nobsf - n1f, nmiss = (float)I - nobsf;
+
+      // ---- per-person posterior and draw -----------------------------------
+      float amu[D], invS[D], sd[D], th[D], epsv[D], alv[D];
+      float tsum = 0.0f, term = 0.0f, bound = bmaxv;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float S = fmaf(n0f, tau[0][d], fmaf(n1f, tau[1][d], nmiss * prior_tau));
+        const float N = fmaf(n0f, mt[0][d], n1f * mt[1][d]);
+        invS[d] = __fdividef(1.0f, S);           // = exp(logvar)
+        amu[d] = N * invS[d];
+        alv[d] = -kLn2 * lg2_approx(S);          // log(1 / S)
+        sd[d] = rsqrtf(S);                       // exp(logvar / 2)
+        epsv[d] = __uint_as_float(lds32(ep + d * 4));
+        th[d] = fmaf(epsv[d], sd[d], amu[d]);
+        tsum += th[d];
+        bound = MODEL == 1 ? bound + fabsf(th[d]) : fmaf(fabsf(th[d]), amaxv[MODEL == 1 ? 0 : d], bound);
+        if (p.form == VIBO_ELBO_KL) {
+          term += -0.5f * (1.0f + alv[d] - amu[d] * amu[d] - invS[d]);
+        } else {
+          term += -0.5f * th[d] * th[d] + 0.5f * epsv[d] * epsv[d] + 0.5f * alv[d];
+        }
+      }
+      if (valid && q == 0) {
+        term_acc += term;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          if (GRAD) asm volatile("st.shared.f32 [%0], %1;" ::"r"(thb + (uint32_t)(r * D + d) * 4), "f"(th[d]) : "memory");
+        }
+        if (p.out_mu != nullptr) {
+          const int64_t row = c * R + r;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            p.out_mu[row * D + d] = amu[d];
+            p.out_lv[row * D + d] = alv[d];
+            p.out_theta[row * D + d] = th[d];
+          }
+        }
+      }
+      // a row can reach the eps32 clamp only if its logit bound exceeds it
+      // (NaN bounds, e.g. all-missing rows under --drop-missing, go exact)
+      const bool exact = !__all_sync(0xffffffffu, bound <= kLogitClamp);
+
+      // ---- pass 2 -----------------------------------------------------------
+      float gth[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) gth[d] = 0.0f;
+      float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+      if (valid) {
+        if (full_obs && !exact)
+          f2_pass2<MODEL, D, LPP, NG, GRAD, true, false>(xp, mp, pp, n_groups, kfull, has_tail, th, tsum, gth, s1, s2, s3);
+        else if (full_obs)
+          f2_pass2<MODEL, D, LPP, NG, GRAD, true, true>(xp, mp, pp, n_groups, kfull, has_tail, th, tsum, gth, s1, s2, s3);
+        else
+          f2_pass2<MODEL, D, LPP, NG, GRAD, false, true>(xp, mp, pp, n_groups, kfull, has_tail, th, tsum, gth, s1, s2, s3);
+        ll_acc += s1 - 0.5f * s2 - kLn2 * s3;
+      }
+
+      // ---- per-person backward ---------------------------------------------
+      if (GRAD) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          float gv = MODEL == 1 ? gth[0] : gth[d];
+#pragma unroll
+          for (int o = LPP / 2; o > 0; o >>= 1) gv += __shfl_xor_sync(0xffffffffu, gv, o);
+          float g_mu, g_lv;
+          if (p.form == VIBO_ELBO_KL) {
+            g_mu = fmaf(p.beta, amu[d], gv);
+            g_lv = 0.5f * gv * epsv[d] * sd[d] + 0.5f * p.beta * (invS[d] - 1.0f);
+          } else {
+            gv += th[d];
+            g_mu = gv;
+            g_lv = 0.5f * gv * epsv[d] * sd[d] - 0.5f;
+          }
+          const float GN = g_mu * invS[d];
+          const float GS = -(g_mu * amu[d] + g_lv) * invS[d];
+          if (valid && q == 0) {
+            tA[0][d] = fmaf(n0f, GN, tA[0][d]);
+            tA[1][d] = fmaf(n1f, GN, tA[1][d]);
+            tB[0][d] = fmaf(n0f, GS, tB[0][d]);
+            tB[1][d] = fmaf(n1f, GS, tB[1][d]);
+          }
+        }
+      }
+    }
+
+    // ======================= phase B: one thread per item group =============
+    if (GRAD) {
+      team_barrier(team);  // every row's d ll / d z and theta are in shared memory
+#pragma unroll
+      for (int k = 0; k < NGB; ++k) {
+        const int g = tt + kF2TeamThreads * k;
+        if (g < n_groups) {
+          uint32_t a = sb + (uint32_t)g * 16;
+          for (int r = 0; r < rows; ++r, a += (uint32_t)I * 4) {
+            const float4 dz = lds128(a);
+            const float dzs[4] = {dz.x, dz.y, dz.z, dz.w};
+            float thr[D];
+#pragma unroll
+            for (int d = 0; d < DA; ++d) thr[d] = __uint_as_float(lds32(thb + (uint32_t)(r * D + d) * 4));
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+              for (int d = 0; d < DA; ++d) acc[(k * 4 + ci) * F + d] = fmaf(dzs[ci], thr[d], acc[(k * 4 + ci) * F + d]);
+              acc[(k * 4 + ci) * F + DA] += dzs[ci];
+            }
+          }
+        }
+      }
+    }
+
+    // the last warp of the team to leave the stage refills it
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      last = atomicAdd(&t_done[s], 1) == TW - 1;
+      if (last) atomicExch(&t_done[s], 0);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      const int64_t cn = c + (int64_t)NS * chunk_step;
+      if (cn < n_chunks) fused_issue_chunk<D>(p, L, cn, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
+    }
+    if (++s == NS) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+
+  // ---- CTA-level combine (deterministic order) -----------------------------
+  __syncthreads();  // every stage consumed; stage memory is free for reuse
+  double* s_d = reinterpret_cast<double*>(smem + L.stage_off);          // [warps][2]
+  float* s_t = reinterpret_cast<float*>(smem + L.stage_off + 1024);     // [warps][4D]
+  float* s_item = reinterpret_cast<float*>(smem + L.stage_off + 4096);  // [I*F]
+  {
+    const double a = warp_sum((double)ll_acc), b = warp_sum((double)term_acc);
+    if (lane == 0) {
+      s_d[warp * 2] = a;
+      s_d[warp * 2 + 1] = b;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float v0 = warp_sum(tA[0][d]), v1 = warp_sum(tA[1][d]), v2 = warp_sum(tB[0][d]),
+                  v3 = warp_sum(tB[1][d]);
+      if (lane == 0) {
+        s_t[warp * 4 * D + d] = v0;
+        s_t[warp * 4 * D + D + d] = v1;
+        s_t[warp * 4 * D + 2 * D + d] = v2;
+        s_t[warp * 4 * D + 3 * D + d] = v3;
+      }
+    }
+  }
+  if (GRAD)
+    for (int k = threadIdx.x; k < I * F; k += blockDim.x) s_item[k] = 0.0f;
+  __syncthreads();
+  if (GRAD) {
+    for (int t = 0; t < NQ; ++t) {
+      if (team == t) {
+#pragma unroll
+        for (int k = 0; k < NGB; ++k) {
+          const int g = tt + kF2TeamThreads * k;
+          if (g < n_groups) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+              for (int f = 0; f < F; ++f) s_item[(size_t)(4 * g + ci) * F + f] += acc[(k * 4 + ci) * F + f];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    float* dst = p.part_item + (size_t)blockIdx.x * I * F;
+    for (int k = threadIdx.x; k < I * F; k += blockDim.x) dst[k] = s_item[k];
+  }
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < kF2Warps; ++w) {
+      a += s_d[w * 2];
+      b += s_d[w * 2 + 1];
+    }
+    p.part_scalar[(size_t)blockIdx.x * 2] = a;
+    p.part_scalar[(size_t)blockIdx.x * 2 + 1] = b;
+  }
+  if (GRAD && threadIdx.x < 4 * D) {
+    float v = 0.0f;
+    for (int w = 0; w < kF2Warps; ++w) v += s_t[w * 4 * D + threadIdx.x];
+    p.part_table[(size_t)blockIdx.x * 4 * D + threadIdx.x] = v;
+  }
+}
+
+template <int MODEL, int D>
+cudaError_t launch_fused2_md(const FusedParams& p, int grid, size_t smem, bool grad, cudaStream_t st);
+
+template <int MODEL, int D, int LPP, int NG>
+static cudaError_t launch_fused2_cfg(const FusedParams& p, int grid, size_t smem, bool grad, cudaStream_t st) {
+  static size_t smem_set[2] = {0, 0};
+  cudaError_t e;
+  if (grad) {
+    auto k = fused2_kernel<MODEL, D, LPP, NG, true>;
+    if (smem > smem_set[1]) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      smem_set[1] = smem;
+    }
+    k<<<grid, kF2Threads, smem, st>>>(p);
+  } else {
+    auto k = fused2_kernel<MODEL, D, LPP, NG, false>;
+    if (smem > smem_set[0]) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      smem_set[0] = smem;
+    }
+    k<<<grid, kF2Threads, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+#define VIBO_FUSED2_INSTANTIATE(MODEL, D)                                                             \
+  template <>                                                                                         \
+  cudaError_t launch_fused2_md<MODEL, D>(const FusedParams& p, int grid, size_t smem, bool grad,      \
+                                         cudaStream_t st) {                                           \
+    int lpp, ng;                                                                                      \
+    fused_pick(p.I, &lpp, &ng);                                                                       \
+    if (lpp == 8 && ng == 4) return launch_fused2_cfg<MODEL, D, 8, 4>(p, grid, smem, grad, st);       \
+    if (lpp == 8 && ng == 8) return launch_fused2_cfg<MODEL, D, 8, 8>(p, grid, smem, grad, st);       \
+    if (lpp == 16 && ng == 4) return launch_fused2_cfg<MODEL, D, 16, 4>(p, grid, smem, grad, st);     \
+    if (lpp == 16 && ng == 8) return launch_fused2_cfg<MODEL, D, 16, 8>(p, grid, smem, grad, st);     \
+    if (lpp == 32 && ng == 4) return launch_fused2_cfg<MODEL, D, 32, 4>(p, grid, smem, grad, st);     \
+    return launch_fused2_cfg<MODEL, D, 32, 8>(p, grid, smem, grad, st);                               \
+  }
+
+}  // namespace vibo

@@ -1,0 +1,5 @@
+// fused2_kernel (two-phase) instantiations for the 1PL model, ability_dim 1.
+#include "vibo_fused2_kernel.cuh"
+namespace vibo {
+VIBO_FUSED2_INSTANTIATE(1, 1)
+}  // namespace vibo

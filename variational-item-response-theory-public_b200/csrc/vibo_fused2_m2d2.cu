@@ -1,0 +1,5 @@
+// fused2_kernel (two-phase) instantiations for the 2PL model, ability_dim 2.
+#include "vibo_fused2_kernel.cuh"
+namespace vibo {
+VIBO_FUSED2_INSTANTIATE(2, 2)
+}  // namespace vibo

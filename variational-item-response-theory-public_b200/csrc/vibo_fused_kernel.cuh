@@ -33,15 +33,22 @@ namespace vibo {
 
 constexpr int kFusedConsumerWarps = 16;
 constexpr int kFusedThreads = kFusedConsumerWarps * 32;
+// The warps of a CTA form kFusedTeams independent teams; each team streams its
+// own interleaved sequence of row chunks through its own ring of stages, so a
+// CTA keeps several smaller bulk copies in flight at staggered times instead
+// of one large one.
+constexpr int kFusedTeamWarps = 4;
+constexpr int kFusedTeams = kFusedConsumerWarps / kFusedTeamWarps;
 
 struct FusedParams {
   int64_t P;
   int I;
-  int R;        // rows per stage (multiple of 16)
-  int nstage;   // ring depth
+  int R;        // rows per stage
+  int nstage;   // ring depth per team
   int form;     // VIBO_ELBO_*
   int missing_policy;
   float beta;
+  int debug;    // 0 normal; 1 stream only (no math); 2 math only (no refills)  [VIBO_FUSED_DEBUG]
   const float* resp;
   const uint8_t* mask;
   const float* eps;        // (P, D)
@@ -68,7 +75,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -77,10 +84,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
+      "}" ::"r"(bar_addr),
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
 // 1-D TMA bulk copy global -> shared, completing `bytes` on `bar`.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -88,6 +96,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
           smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+// Shared-memory loads by 32-bit shared-window address (+ immediate offset):
+// keeps one base register per operand instead of letting the compiler
+// re-derive the generic->shared conversion for every group.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -111,16 +132,17 @@ __host__ __device__ inline size_t fused_align(size_t v, size_t a) { return (v + 
 struct FusedSmem {
   size_t params_off, stage_off, stage_bytes, resp_bytes, mask_off, eps_off, total;
 };
-__host__ __device__ inline FusedSmem fused_smem_layout(int I, int D, int model, int R, int nstage) {
+__host__ __device__ inline FusedSmem fused_smem_layout(int I, int D, int model, int R, int nstage,
+                                                       int nteams = kFusedTeams, int scratch_bytes = 0) {
   FusedSmem L;
   const int nparam = model == 1 ? 1 : (model == 2 ? D + 1 : D + 2);
-  L.params_off = 128;
+  L.params_off = 256 + scratch_bytes;  // [0,128): up to 16 mbarriers; [128,192): up to 16 stage counters
   L.stage_off = fused_align(L.params_off + (size_t)nparam * I * 4, 128);
   L.resp_bytes = (size_t)R * I * 4;
   L.mask_off = L.resp_bytes;
   L.eps_off = fused_align(L.mask_off + (size_t)R * I, 16);
   L.stage_bytes = fused_align(L.eps_off + (size_t)R * D * 4, 128);
-  L.total = L.stage_off + (size_t)nstage * L.stage_bytes;
+  L.total = L.stage_off + (size_t)nstage * nteams * L.stage_bytes;
   return L;
 }
 
@@ -156,104 +178,118 @@ __device__ __forceinline__ void fused_issue_chunk(const FusedParams& p, const Fu
   }
 }
 
-// Pass 2 over one person's row: link, Bernoulli log-likelihood and (GRAD) the
-// per-cell gradient terms.  FULL: every cell of the row is observed, so the
-// mask is not consulted and the 0/1 response bits drive a sign flip directly.
-//   accM += max(-t, 0), accL += log2(1 + 2^(-|t| log2 e))   => ll = -(accM + ln2 accL)
-template <int MODEL, int D, int LPP, int NG, bool GRAD, bool FULL>
-__device__ __forceinline__ void fused_pass2(const float* __restrict__ xr, const uint8_t* __restrict__ mr,
-                                            const float* __restrict__ s_param, int I, int n_groups, int q,
+// One group of 4 consecutive items of one person: link, Bernoulli
+// log-likelihood and (GRAD) the per-cell gradient terms.
+//
+// 1PL/2PL, with zc = clamp(z, +-kLogitClamp) (the eps32 clamp of
+// torch.distributions in logit space) and e = exp(-|zc|):
+//   ll = x zc - softplus(zc) = (x - 1/2) zc - |zc|/2 - log(1 + e)
+//   d ll / d z = x - sigmoid(zc) = (x - 1/2) - copysign(1/(1+e) - 1/2, zc),  0 where z != zc
+// accumulated as s1 += (x-1/2) zc, s2 += |zc|, s3 += log2(1+e).
+// FULL: every cell of the row is observed (mask not consulted).  Otherwise a
+// missing cell is turned into the neutral cell (x = 1/2, z = 0), whose only
+// contribution -- log2(2) = 1 to s3 -- is subtracted via the caller's count.
+template <int MODEL, int D, bool GRAD, bool FULL>
+__device__ __forceinline__ void fused_group(const float4& x4, uint32_t m4, const float4& b4,
+                                            const float4 (&a4)[MODEL == 1 ? 1 : D], const float4& g4,
                                             const float (&th)[D], float tsum, float (&gth)[D],
-                                            float (&acc)[GRAD ? NG * 4 * item_width(MODEL, D) : 1],
-                                            float& accM, float& accL, float& ll3) {
+                                            float* __restrict__ acc, float& s1, float& s2, float& s3) {
   constexpr int F = item_width(MODEL, D);
   constexpr int DA = MODEL == 1 ? 0 : D;
   constexpr float kNegLog2e = -1.4426950408889634f;
-  const float* s_b = s_param + (size_t)DA * I;
-  const float* s_g = s_param + (size_t)(DA + 1) * I;
+  const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+  const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
+  const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-  for (int k = 0; k < NG; ++k) {
-    const int g = q + LPP * k;
-    if (g < n_groups) {
-      const float4 x4 = *reinterpret_cast<const float4*>(xr + 4 * g);
-      uint32_t m4 = 0x01010101u;
-      if (!FULL) m4 = *reinterpret_cast<const uint32_t*>(mr + 4 * g);
-      const float4 b4 = *reinterpret_cast<const float4*>(s_b + 4 * g);
-      float4 a4[DA > 0 ? DA : 1];
+  for (int c = 0; c < 4; ++c) {
+    float av[DA > 0 ? DA : 1];
 #pragma unroll
-      for (int d = 0; d < DA; ++d) a4[d] = *reinterpret_cast<const float4*>(s_param + (size_t)d * I + 4 * g);
-      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (MODEL == 3) g4 = *reinterpret_cast<const float4*>(s_g + 4 * g);
-      const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-      const float bs[4] = {b4.x, b4.y, b4.z, b4.w};
-      const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+    for (int d = 0; d < DA; ++d) av[d] = c == 0 ? a4[d].x : (c == 1 ? a4[d].y : (c == 2 ? a4[d].z : a4[d].w));
+    float z = bs[c];
+    if (MODEL == 1) {
+      z += tsum;
+    } else {
 #pragma unroll
-      for (int cidx = 0; cidx < 4; ++cidx) {
-        float av[DA > 0 ? DA : 1];
+      for (int d = 0; d < DA; ++d) z = fmaf(-th[d], av[d], z);
+    }
+    const bool o = FULL ? true : ((m4 >> (8 * c)) & 0xffu) != 0;
+    float dz = 0.0f, dgam = 0.0f;
+    if (MODEL == 3) {
+      const CellGrad cg = cell_3pl<false>(z, gs[c], xs[c] > 0.5f);
+      s1 += o ? cg.ll : 0.0f;
+      dz = o ? cg.dz : 0.0f;
+      dgam = o ? cg.dgam : 0.0f;
+    } else {
+      float xm = xs[c] - 0.5f;
+      if (!FULL) {
+        xm = o ? xm : 0.0f;
+        z = o ? z : 0.0f;
+      }
+      const float zc = fminf(fmaxf(z, -kLogitClamp), kLogitClamp);
+      const float e = ex2_approx(fabsf(zc) * kNegLog2e);
+      const float w = 1.0f + e;
+      s1 = fmaf(xm, zc, s1);
+      s2 += fabsf(zc);
+      s3 += lg2_approx(w);
+      if (GRAD) {
+        const float h = rcp_approx(w) - 0.5f;                    // sigmoid(|zc|) - 1/2
+        const float cs = __uint_as_float((__float_as_uint(h) & 0x7fffffffu) | (__float_as_uint(zc) & 0x80000000u));
+        dz = (z == zc) ? xm - cs : 0.0f;                         // zero outside the eps32 clamp
+      }
+    }
+    if (GRAD) {
+      if (MODEL == 1) {
+        gth[0] -= dz;  // d loss_k / d theta_d = -sum_j dz (same for every d)
+        acc[c * F] += dz;
+      } else {
 #pragma unroll
-        for (int d = 0; d < DA; ++d)
-          av[d] = cidx == 0 ? a4[d].x : (cidx == 1 ? a4[d].y : (cidx == 2 ? a4[d].z : a4[d].w));
-        float z = bs[cidx];
-        if (MODEL == 1) {
-          z += tsum;
-        } else {
-#pragma unroll
-          for (int d = 0; d < DA; ++d) z = fmaf(-th[d], av[d], z);
+        for (int d = 0; d < DA; ++d) {
+          gth[d] = fmaf(dz, av[d], gth[d]);
+          acc[c * F + d] = fmaf(dz, th[d], acc[c * F + d]);
         }
-        const bool o = FULL ? true : ((m4 >> (8 * cidx)) & 0xffu) != 0;
-        float dz = 0.0f, dgam = 0.0f;
-        if (MODEL == 3) {
-          const CellGrad cg = cell_3pl<false>(z, gs[cidx], xs[cidx] > 0.5f);
-          ll3 += o ? cg.ll : 0.0f;
-          dz = o ? cg.dz : 0.0f;
-          dgam = o ? cg.dgam : 0.0f;
-        } else {
-          // u = (2x - 1) z : FULL uses the exponent bit of the 0/1 float
-          uint32_t flip = 0;
-          bool x1 = true;
-          float u;
-          if (FULL) {
-            flip = (~(__float_as_uint(xs[cidx]) << 2)) & 0x80000000u;  // 0 if x == 1, sign bit if x == 0
-            u = __uint_as_float(__float_as_uint(z) ^ flip);
-          } else {
-            x1 = xs[cidx] > 0.5f;
-            u = x1 ? z : -z;
-          }
-          const float t = fminf(fmaxf(u, -kLogitClamp), kLogitClamp);
-          const float e = ex2_approx(fabsf(t) * kNegLog2e);
-          const float w = 1.0f + e;
-          const float lw = lg2_approx(w);
-          if (FULL) {
-            accM += fmaxf(-t, 0.0f);
-            accL += lw;
-          } else {
-            accM += o ? fmaxf(-t, 0.0f) : 0.0f;
-            accL += o ? lw : 0.0f;
-          }
-          if (GRAD) {
-            const float sig = (t >= 0.0f ? e : 1.0f) * rcp_approx(w);  // sigmoid(-t)
-            const float du = (t == u && o) ? sig : 0.0f;               // zero outside the eps32 clamp
-            dz = FULL ? __uint_as_float(__float_as_uint(du) ^ flip) : (x1 ? du : -du);
-          }
-        }
-        if (GRAD) {
-          const int slot = (k * 4 + cidx) * F;
-          if (MODEL == 1) {
-            gth[0] -= dz;  // d loss_k / d theta_d = -sum_j dz (same for every d)
-            acc[slot] += dz;
-          } else {
-#pragma unroll
-            for (int d = 0; d < DA; ++d) {
-              gth[d] = fmaf(dz, av[d], gth[d]);
-              acc[slot + d] = fmaf(dz, th[d], acc[slot + d]);
-            }
-            acc[slot + D] += dz;
-            if (MODEL == 3) acc[slot + D + 1] += dgam;
-          }
-        }
+        acc[c * F + D] += dz;
+        if (MODEL == 3) acc[c * F + D + 1] += dgam;
       }
     }
   }
+}
+
+// Pass 2 over one person's row.  Lane q owns groups q + LPP*k: the first
+// `kfull` of them are valid for every lane (warp-uniform test, no divergence);
+// at most one further group is valid for lanes q < ntail only, and it always
+// accumulates into the last register slot (slot NG-1 is free whenever a
+// ragged group exists).
+template <int MODEL, int D, int LPP, int NG, bool GRAD, bool FULL>
+__device__ __forceinline__ void fused_pass2(uint32_t xp, uint32_t mp, uint32_t pp, int I4, int kfull, bool has_tail,
+                                            const float (&th)[D], float tsum, float (&gth)[D],
+                                            float (&acc)[GRAD ? NG * 4 * item_width(MODEL, D) : 1],
+                                            float& s1, float& s2, float& s3) {
+  constexpr int F = item_width(MODEL, D);
+  constexpr int DA = MODEL == 1 ? 0 : D;
+  float nmiss_lane = 0.0f;
+  // xp / mp / pp: shared-window byte addresses of this lane's first group in the
+  // response row, the mask row and the item-parameter arrays (I4 float4 each)
+  auto one = [&](int gi, int slot) {
+    const float4 x4 = lds128(xp + gi * 16);
+    uint32_t m4 = 0x01010101u;
+    if (!FULL) {
+      m4 = lds32(mp + gi * 4);
+      if (MODEL != 3) nmiss_lane += (float)(4 - __popc(m4 & 0x01010101u));
+    }
+    float4 a4[DA > 0 ? DA : 1];
+#pragma unroll
+    for (int d = 0; d < DA; ++d) a4[d] = lds128(pp + (d * I4 + gi) * 16);
+    const float4 b4 = lds128(pp + (DA * I4 + gi) * 16);
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODEL == 3) g4 = lds128(pp + ((DA + 1) * I4 + gi) * 16);
+    fused_group<MODEL, D, GRAD, FULL>(x4, m4, b4, a4, g4, th, tsum, gth, GRAD ? &acc[slot * 4 * F] : &acc[0],
+                                      s1, s2, s3);
+  };
+#pragma unroll
+  for (int k = 0; k < NG; ++k)
+    if (k < kfull) one(LPP * k, k);
+  if (has_tail) one(LPP * kfull, NG - 1);
+  if (!FULL && MODEL != 3) s3 -= nmiss_lane;  // neutral cells added log2(2) each
 }
 
 template <int MODEL, int D, int LPP, int NG, bool GRAD>
@@ -269,17 +305,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
   extern __shared__ __align__(128) unsigned char smem[];
   const int I = p.I, R = p.R, NS = p.nstage;
   const FusedSmem L = fused_smem_layout(I, D, MODEL, R, NS);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-  int* done_cnt = reinterpret_cast<int*>(full_bar + 8);  // warps finished with each stage
+  constexpr int TW = kFusedTeamWarps, NQ = kFusedTeams;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);     // [NQ * NS]
+  int* done_cnt = reinterpret_cast<int*>(smem + 128);          // warps finished with each stage
   float* s_param = reinterpret_cast<float*>(smem + L.params_off);  // [a_0 | .. | a_{D-1} | b | guess]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = warp / TW, wt = warp % TW;
   const int n_groups = I >> 2;
   const int64_t n_chunks = (p.P + R - 1) / R;
+  // team t of CTA b walks chunks (b*NQ + t) + k * (gridDim.x * NQ)
+  const int64_t chunk0 = (int64_t)blockIdx.x * NQ + team, chunk_step = (int64_t)gridDim.x * NQ;
+  uint64_t* t_full = full_bar + team * NS;
+  int* t_done = done_cnt + team * NS;
+  unsigned char* t_stage = smem + L.stage_off + (size_t)team * NS * L.stage_bytes;
 
   // ---- one-time setup ----------------------------------------------------
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NQ * NS; ++s) {
       mbar_init(&full_bar[s], 1);
       done_cnt[s] = 0;
     }
@@ -298,7 +341,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
   __syncthreads();
 
   // per-CTA results
-  double ll_acc = 0.0, term_acc = 0.0;
+  // per-lane float accumulators (a few hundred rows each; the cross-lane and
+  // cross-CTA sums are done in double)
+  float ll_acc = 0.0f, term_acc = 0.0f;
   float tA[2][D], tB[2][D];
   float acc[GRAD ? IPL * F : 1];
 #pragma unroll
@@ -306,12 +351,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
 #pragma unroll
   for (int k = 0; k < (GRAD ? IPL * F : 1); ++k) acc[k] = 0.0f;
 
-  // prologue: the first NS chunks of this CTA
-  if (warp == 0) {
+  // prologue: the first NS chunks of each team
+  if (wt == 0) {
     for (int s = 0; s < NS; ++s) {
-      const int64_t c = blockIdx.x + (int64_t)s * gridDim.x;
-      if (c < n_chunks)
-        fused_issue_chunk<D>(p, L, c, smem + L.stage_off + (size_t)s * L.stage_bytes, &full_bar[s], lane);
+      const int64_t c = chunk0 + (int64_t)s * chunk_step;
+      if (c < n_chunks) fused_issue_chunk<D>(p, L, c, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
     }
   }
   {
@@ -328,52 +372,75 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
         mt[r][d] = mu * tau[r][d];
       }
     const float prior_tau = p.missing_policy == VIBO_MISSING_PRIOR ? 1.0f / (1.0f + kPoeEps) : 0.0f;
+    // lane q owns the 4-item groups q + LPP*k: k < kfull for every lane, plus
+    // one ragged group (index kfull) for lanes q < ntail
+    const int kfull = min(n_groups / LPP, NG);
+    const bool has_tail = kfull < NG && q < n_groups - kfull * LPP;
+    uint32_t pp = smem_u32(s_param) + q * 16;
+    asm volatile("mov.u32 %0, %0;" : "+r"(pp));  // opaque: keep it in a register, do not re-derive per group
 
-    int it = 0;
-    for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
-      const int s = it % NS;
-      mbar_wait(&full_bar[s], (it / NS) & 1);
-      const unsigned char* st = smem + L.stage_off + (size_t)s * L.stage_bytes;
+    // Loop state is kept incremental and 32-bit (no divisions, no 64-bit row
+    // arithmetic per stage): ring slot s and its mbarrier phase, the shared
+    // addresses of this sub-group's first row in a stage, and the rows left.
+    const uint32_t stage0 = smem_u32(t_stage), bar0 = smem_u32(t_full);
+    const int first_row = wt * PPW + sub;                       // row of this sub-group in a stage
+    const uint32_t off_x = (uint32_t)first_row * I * 4 + q * 16;
+    const uint32_t off_m = (uint32_t)L.mask_off + (uint32_t)first_row * I + q * 4;
+    const uint32_t off_e = (uint32_t)L.eps_off + (uint32_t)first_row * D * 4;
+    const uint32_t step_x = (uint32_t)TW * PPW * I * 4, step_m = (uint32_t)TW * PPW * I,
+                   step_e = (uint32_t)TW * PPW * D * 4;
+    int s = 0;
+    uint32_t phase = 0;
+    int64_t rows_left = p.P - chunk0 * R;                       // rows from this chunk to the end
+    const int64_t rows_step = chunk_step * R;
+    for (int64_t c = chunk0; c < n_chunks; c += chunk_step, rows_left -= rows_step) {
+      if (p.debug != 2 || c == chunk0) mbar_wait_addr(bar0 + (uint32_t)s * 8, phase);
+      const uint32_t sb = stage0 + (uint32_t)s * (uint32_t)L.stage_bytes;
+      const int rows = rows_left < R ? (int)rows_left : R;
       const int64_t row0 = c * R;
-      const int rows = (int)((p.P - row0 < R) ? p.P - row0 : R);
-      for (int rbase = warp * PPW; rbase < rows; rbase += NW * PPW) {
+      uint32_t xrow = sb + off_x, mrow = sb + off_m, erow = sb + off_e;
+      for (int rbase = wt * PPW; rbase < rows && p.debug != 1;
+           rbase += TW * PPW, xrow += step_x, mrow += step_m, erow += step_e) {
         const int r = rbase + sub;
         const bool valid = r < rows;
-        const int rr = valid ? r : rbase;  // keep addresses in range for idle sub-groups
-        const float* xr = reinterpret_cast<const float*>(st) + (size_t)rr * I;
-        const uint8_t* mr = st + L.mask_off + (size_t)rr * I;
-        const float* er = reinterpret_cast<const float*>(st + L.eps_off) + (size_t)rr * D;
+        // idle sub-groups of a ragged tail re-read the first row of the pass (in range)
+        const uint32_t xp = valid ? xrow : xrow - (uint32_t)sub * I * 4;
+        const uint32_t mp = valid ? mrow : mrow - (uint32_t)sub * I;
+        const uint32_t ep = valid ? erow : erow - (uint32_t)sub * D * 4;
 
         // ---- pass 1: counts ------------------------------------------------
         float n1f = 0.0f;
         uint32_t mand = 0x01010101u;
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-          const int g = q + LPP * k;
-          if (g < n_groups) {
-            const float4 x = *reinterpret_cast<const float4*>(xr + 4 * g);
-            const uint32_t m = *reinterpret_cast<const uint32_t*>(mr + 4 * g);
+          if (k < kfull) {
+            const float4 x = lds128(xp + LPP * k * 16);
             n1f += (x.x + x.y) + (x.z + x.w);
-            mand &= m;
+            mand &= lds32(mp + LPP * k * 4);
           }
+        }
+        if (has_tail) {
+          const float4 x = lds128(xp + LPP * kfull * 16);
+          n1f += (x.x + x.y) + (x.z + x.w);
+          mand &= lds32(mp + LPP * kfull * 4);
         }
         const bool full_obs = __all_sync(0xffffffffu, mand == 0x01010101u);
         float nobsf = (float)I;
         if (!full_obs) {
           int n1 = 0, nobs = 0;
+          auto count = [&](int gi) {
+            const float4 x = lds128(xp + gi * 16);
+            const uint32_t m = lds32(mp + gi * 4);
+            const bool o0 = (m & 0xffu) != 0, o1 = (m & 0xff00u) != 0, o2 = (m & 0xff0000u) != 0,
+                       o3 = (m & 0xff000000u) != 0;
+            nobs += (int)o0 + (int)o1 + (int)o2 + (int)o3;
+            n1 += (int)(o0 && x.x > 0.5f) + (int)(o1 && x.y > 0.5f) + (int)(o2 && x.z > 0.5f) +
+                  (int)(o3 && x.w > 0.5f);
+          };
 #pragma unroll
-          for (int k = 0; k < NG; ++k) {
-            const int g = q + LPP * k;
-            if (g < n_groups) {
-              const float4 x = *reinterpret_cast<const float4*>(xr + 4 * g);
-              const uint32_t m = *reinterpret_cast<const uint32_t*>(mr + 4 * g);
-              const bool o0 = (m & 0xffu) != 0, o1 = (m & 0xff00u) != 0, o2 = (m & 0xff0000u) != 0,
-                         o3 = (m & 0xff000000u) != 0;
-              nobs += (int)o0 + (int)o1 + (int)o2 + (int)o3;
-              n1 += (int)(o0 && x.x > 0.5f) + (int)(o1 && x.y > 0.5f) + (int)(o2 && x.z > 0.5f) +
-                    (int)(o3 && x.w > 0.5f);
-            }
-          }
+          for (int k = 0; k < NG; ++k)
+            if (k < kfull) count(LPP * k);
+          if (has_tail) count(LPP * kfull);
           n1f = (float)n1;
           nobsf = (float)nobs;
         }
@@ -397,7 +464,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
           amu[d] = N * invS;
           alv[d] = -kLn2 * lg2_approx(S);          // log(1 / S)
           sd[d] = rsqrtf(S);                       // exp(logvar / 2)
-          epsv[d] = er[d];
+          epsv[d] = __uint_as_float(lds32(ep + d * 4));
           th[d] = fmaf(epsv[d], sd[d], amu[d]);
           tsum += th[d];
           if (p.form == VIBO_ELBO_KL) {
@@ -408,7 +475,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
           }
         }
         if (valid && q == 0) {
-          term_acc += (double)term;
+          term_acc += term;
           const int64_t row = row0 + r;
           if (p.out_mu != nullptr) {
 #pragma unroll
@@ -424,15 +491,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
         float gth[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) gth[d] = 0.0f;
-        float accM = 0.0f, accL = 0.0f, ll3 = 0.0f;
+        float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
         if (!valid) {
           // idle sub-group of a ragged tail: contributes nothing (its lanes
           // still take part in the shuffles below)
         } else if (full_obs)
-          fused_pass2<MODEL, D, LPP, NG, GRAD, true>(xr, mr, s_param, I, n_groups, q, th, tsum, gth, acc, accM, accL, ll3);
+          fused_pass2<MODEL, D, LPP, NG, GRAD, true>(xp, mp, pp, n_groups, kfull, has_tail, th, tsum, gth, acc, s1, s2, s3);
         else
-          fused_pass2<MODEL, D, LPP, NG, GRAD, false>(xr, mr, s_param, I, n_groups, q, th, tsum, gth, acc, accM, accL, ll3);
-        if (valid) ll_acc += (double)(MODEL == 3 ? ll3 : -(accM + kLn2 * accL));
+          fused_pass2<MODEL, D, LPP, NG, GRAD, false>(xp, mp, pp, n_groups, kfull, has_tail, th, tsum, gth, acc, s1, s2, s3);
+        if (valid) ll_acc += MODEL == 3 ? s1 : s1 - 0.5f * s2 - kLn2 * s3;
 
         // ---- per-person backward -------------------------------------------
         if (GRAD) {
@@ -461,19 +528,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
           }
         }
       }
-      // the last warp to leave the stage refills it with the chunk NS iterations ahead
+      // the last warp of the team to leave the stage refills it with the chunk NS iterations ahead
       __syncwarp();
       int last = 0;
       if (lane == 0) {
         __threadfence_block();
-        last = atomicAdd(&done_cnt[s], 1) == NW - 1;
-        if (last) atomicExch(&done_cnt[s], 0);
+        last = atomicAdd(&t_done[s], 1) == TW - 1;
+        if (last) atomicExch(&t_done[s], 0);
       }
       last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        const int64_t cn = c + (int64_t)NS * gridDim.x;
-        if (cn < n_chunks)
-          fused_issue_chunk<D>(p, L, cn, smem + L.stage_off + (size_t)s * L.stage_bytes, &full_bar[s], lane);
+      if (last && p.debug != 2) {
+        const int64_t cn = c + (int64_t)NS * chunk_step;
+        if (cn < n_chunks) fused_issue_chunk<D>(p, L, cn, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
+      }
+      if (p.debug != 2) {
+        if (++s == NS) {
+          s = 0;
+          phase ^= 1u;
+        }
       }
     }
   }
@@ -484,7 +556,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
   float* s_t = reinterpret_cast<float*>(smem + L.stage_off + 1024);     // [NW+1][4D]
   float* s_item = reinterpret_cast<float*>(smem + L.stage_off + 4096);  // [I*F]
   {
-    const double a = warp_sum(ll_acc), b = warp_sum(term_acc);
+    const double a = warp_sum((double)ll_acc), b = warp_sum((double)term_acc);
     if (lane == 0) {
       s_d[warp * 2] = a;
       s_d[warp * 2 + 1] = b;
@@ -514,10 +586,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
   if (GRAD) {
     for (int w = 0; w < NW; ++w) {
       if (warp == w && lane < LPP) {
+        const int kf = min(n_groups / LPP, NG);
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-          const int g = lane + LPP * k;
-          if (g < n_groups) {
+          // slot k holds group lane + LPP*k, except that the last slot holds the ragged group
+          const int g = lane + LPP * ((k == NG - 1 && kf < NG) ? kf : k);
+          if ((k < kf || k == NG - 1) && g < n_groups) {
 #pragma unroll
             for (int cidx = 0; cidx < 4; ++cidx)
 #pragma unroll
@@ -553,14 +627,22 @@ cudaError_t launch_fused_md(const FusedParams& p, int grid, size_t smem, bool gr
 
 template <int MODEL, int D, int LPP, int NG>
 static cudaError_t launch_fused_cfg(const FusedParams& p, int grid, size_t smem, bool grad, cudaStream_t st) {
+  // opt in to > 48 KB dynamic shared memory once per kernel (and per growth)
+  static size_t smem_set[2] = {0, 0};
   cudaError_t e;
   if (grad) {
     auto k = fused_uncond_kernel<MODEL, D, LPP, NG, true>;
-    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if (smem > smem_set[1]) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      smem_set[1] = smem;
+    }
     k<<<grid, kFusedThreads, smem, st>>>(p);
   } else {
     auto k = fused_uncond_kernel<MODEL, D, LPP, NG, false>;
-    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if (smem > smem_set[0]) {
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      smem_set[0] = smem;
+    }
     k<<<grid, kFusedThreads, smem, st>>>(p);
   }
   return cudaGetLastError();

@@ -409,6 +409,10 @@ __global__ void bernoulli_ll_kernel(int64_t n, const float* __restrict__ resp,
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+void note_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 static int g_sm_count = 0;
 int sm_count() {
   if (g_sm_count == 0) {
@@ -444,6 +448,7 @@ static cudaError_t launch_encode_d(const vibo_desc& d, const float* resp, const 
   const size_t smem = (size_t)kRowsPerTile * ns * 2 * D * sizeof(float);
   encode_kernel<D, M><<<grid, ns * 32, smem, st>>>(d.num_person, d.num_item, d.conditional,
                                                    d.missing_policy, resp, mask, table, mu, lv, S);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -462,6 +467,7 @@ static cudaError_t launch_encode_bwd_d(const vibo_desc& d, const float* resp, co
   const int n = 2 * (d.conditional ? d.num_item : 1) * D;
   encode_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(d.num_item, D, d.conditional, grid,
                                                               part, table, g_table);
+  note_launch(2);
   return cudaGetLastError();
 }
 
@@ -485,9 +491,11 @@ static cudaError_t launch_link_dm(const vibo_desc& d, const float* resp, const u
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+  note_launch(2);
   if (g_item != nullptr) {
     const int n = d.num_item * F;
     sum_partials_f32_kernel<<<(n + 127) / 128, 128, 0, st>>>(part_g, grid, n, 1.0f, g_item);
+    note_launch();
   }
   return cudaGetLastError();
 }
@@ -559,6 +567,7 @@ cudaError_t launch_decode(const vibo_desc& d, const float* ability, const float*
     case 3: decode_kernel<3><<<(int)blocks, 256, 0, st>>>(d.num_person, d.num_item, d.ability_dim, ability, item_feat, out); break;
     default: return cudaErrorInvalidValue;
   }
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -579,6 +588,7 @@ cudaError_t launch_bernoulli_ll(const vibo_desc& d, const float* resp, const uin
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+  note_launch(2);
   return cudaGetLastError();
 }
 

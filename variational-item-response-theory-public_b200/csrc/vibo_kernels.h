@@ -10,6 +10,7 @@
 namespace vibo {
 
 int sm_count();
+void note_launch(int n = 1);  // counts kernel launches (vibo_launch_count)
 int item_width_host(int model, int D);
 int general_max_items(int D);
 int general_grid(int64_t P, int I, int D);
@@ -49,6 +50,9 @@ cudaError_t launch_accumulate(float* dst, const float* src, int n, double* dst2,
 
 // vibo_fused.cu: single-pass kernel.  Returns false when the configuration is
 // not covered (caller composes the general kernels instead).
+void profile_begin();
+int profile_end(int* n, double* total_ms);
+unsigned long long launch_count();
 bool fused_supported(const vibo_desc& d, const float* resp, const uint8_t* mask);
 size_t fused_workspace_bytes(const vibo_desc& d);
 cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* mask,

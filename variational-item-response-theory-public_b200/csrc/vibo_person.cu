@@ -100,6 +100,7 @@ cudaError_t launch_accumulate(float* dst, const float* src, int n, double* dst2,
   if (blocks < 1) blocks = 1;
   if (blocks > 1024) blocks = 1024;
   accumulate_kernel<<<blocks, 256, 0, st>>>(dst, src, n, dst2, src2, n2);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -122,6 +123,7 @@ cudaError_t launch_person_forward(const vibo_desc& d, const float* amu, const fl
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   sum_term_kernel<<<1, 32, 0, st>>>(part_term, grid, out_term);
+  note_launch(2);
   return cudaGetLastError();
 }
 
@@ -132,11 +134,13 @@ cudaError_t launch_person_backward(const vibo_desc& d, float beta, const float* 
   const int64_t n = d.num_person * (int64_t)d.ability_dim;
   person_backward_kernel<<<person_grid(n), 256, 0, st>>>(n, d.elbo_form, beta, amu, alv, eps, ability,
                                                          g_ll_ability, g_mu, g_lv);
+  note_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_negate(float* v, int n, cudaStream_t st) {
   negate_kernel<<<(n + 255) / 256, 256, 0, st>>>(v, n);
+  note_launch();
   return cudaGetLastError();
 }
 

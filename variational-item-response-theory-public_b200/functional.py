@@ -22,7 +22,8 @@ def prepare_rows(response: torch.Tensor, mask: torch.Tensor):
     copy; the int64 mask the reference CLI builds (vibo.py:240) costs one
     conversion pass."""
     if response.dim() == 3:
-        response = response.reshape(response.shape[0], response.shape[1])
+        response = response.view(response.shape[0], response.shape[1]) if response.is_contiguous() \
+            else response.reshape(response.shape[0], response.shape[1])
     if mask.dim() == 3:
         mask = mask.reshape(mask.shape[0], mask.shape[1])
     if response.dtype != torch.float32:
@@ -61,6 +62,36 @@ class FusedElbo(torch.autograd.Function):
             extras.append(out[name] if out[name] is not None else torch.empty(0, device=response.device))
         ctx.mark_non_differentiable(*extras)
         return (loss_k.to(torch.float32), *extras)
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        g_table, g_item = ctx.saved_tensors
+        return None, None, g_loss * g_table, g_loss * g_item, None, None
+
+
+class FusedElboHost(torch.autograd.Function):
+    """FusedElbo with the response / mask rows in HOST memory
+    (vibo_fused_elbo_host): person chunks are streamed host->device inside the
+    call, overlapped with the kernels; the loss comes back in pinned memory."""
+
+    @staticmethod
+    def forward(ctx, response_host, mask_host, table, item_feat, eps_ability, cfg):
+        want = bool(ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        out = K.fused_elbo_host(response_host, mask_host, table.detach().contiguous(),
+                                item_feat.detach().contiguous(), eps_ability,
+                                irt_model=cfg["irt_model"], conditional=cfg["conditional"],
+                                missing_policy=cfg["missing_policy"], elbo_form=cfg["elbo_form"],
+                                beta=cfg["beta"], seed=cfg.get("seed", 0),
+                                person_offset=cfg.get("person_offset", 0), want_grads=want,
+                                chunk_person=cfg.get("chunk_person", 65536),
+                                staging=cfg.get("staging"))
+        cfg["staging"] = out["staging"]  # reused by the next call
+        ll, term = out["scalars"][0], out["scalars"][1]
+        loss_k = (-ll + cfg["beta"] * term) if cfg["elbo_form"] == ELBO_KL else (-ll - term)
+        if want:
+            ctx.save_for_backward(out["g_table"], out["g_item"])
+        ctx.mark_non_differentiable(out["scalars"], out["scalars_host"])
+        return loss_k.to(torch.float32), out["scalars"], out["scalars_host"]
 
     @staticmethod
     def backward(ctx, g_loss, *_):

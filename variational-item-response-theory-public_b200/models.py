@@ -275,6 +275,12 @@ class VIBO_1PL(nn.Module):
         resp, msk = VF.prepare_rows(response, mask)
         P = resp.shape[0]
         item_feat_mu, item_feat_logvar = self.item_encoder()
+        host_rows = (not resp.is_cuda) and item_feat_mu.is_cuda
+        if host_rows:
+            if self.n_norm_flows > 0 or return_outputs:
+                raise NotImplementedError("host-resident rows: flows / return_outputs need device rows")
+            if eps_ability is None and seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         if eps_item is None:
             eps_item = torch.randn_like(item_feat_mu)
         item_feat = eps_item * torch.exp(0.5 * item_feat_logvar) + item_feat_mu
@@ -282,6 +288,7 @@ class VIBO_1PL(nn.Module):
         if eps_ability is None and seed is None:
             eps_ability = torch.randn(P, self.ability_dim, dtype=torch.float32, device=resp.device)
         beta = float(annealing_factor)
+        kl_form = bool(use_kl_divergence)
 
         if self.n_norm_flows > 0:
             return self._flow_elbo(resp, msk, table, item_feat, item_feat_mu, item_feat_logvar,
@@ -292,8 +299,16 @@ class VIBO_1PL(nn.Module):
                    elbo_form=VF.ELBO_KL if use_kl_divergence else VF.ELBO_SAMPLE, beta=beta,
                    seed=0 if seed is None else int(seed), person_offset=int(person_offset),
                    want_person_outputs=return_outputs)
-        loss_k, scalars, a_mu, a_lv, ability = VF.FusedElbo.apply(
-            resp, msk, table, item_feat, eps_ability, cfg)
+        if host_rows:
+            cfg["chunk_person"] = getattr(self, "host_chunk_person", 65536)
+            cfg["staging"] = getattr(self, "_host_staging", None)
+            loss_k, scalars, scalars_host = VF.FusedElboHost.apply(resp, msk, table, item_feat,
+                                                                   eps_ability, cfg)
+            self._host_staging = cfg["staging"]
+            a_mu = a_lv = ability = None
+        else:
+            loss_k, scalars, a_mu, a_lv, ability = VF.FusedElbo.apply(
+                resp, msk, table, item_feat, eps_ability, cfg)
         if use_kl_divergence:
             item_term = beta * kl_divergence_standard_normal_prior(item_feat_mu, item_feat_logvar).sum()
         else:
