@@ -47,6 +47,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void team_barrier(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kF2TeamThreads) : "memory");
 }
@@ -122,9 +127,10 @@ __device__ __forceinline__ void f2_pass2(uint32_t xp, uint32_t mp, uint32_t pp, 
     const float4 b4 = lds128(pp + (DA * I4 + gi) * 16);
     f2_group<MODEL, D, GRAD, FULL, EXACT>(xp + gi * 16, m4, b4, a4, th, tsum, gth, s1, s2, s3);
   };
-#pragma unroll
-  for (int k = 0; k < NG; ++k)
-    if (k < kfull) one(LPP * k);
+  // no per-group register state is indexed by k, so this is a real loop
+  // (warp-uniform trip count), lightly unrolled for instruction-level parallelism
+#pragma unroll 2
+  for (int k = 0; k < kfull; ++k) one(LPP * k);
   if (has_tail) one(LPP * kfull);
   if (!FULL) s3 -= nmiss_lane;  // each neutral cell added log2(2) = 1
 }
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
   for (int k = 0; k < (GRAD ? NGB * 4 * F : 1); ++k) acc[k] = 0.0f;
 
   const int sub = lane / LPP, q = lane % LPP;
+  const uint32_t submask = LPP == 32 ? 0xffffffffu : (((1u << LPP) - 1u) << (sub * LPP));
   float tau[2][D], mt[2][D], amaxv[DA > 0 ? DA : 1];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
@@ -259,25 +266,23 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
       const uint32_t ep = valid ? erow : erow - (uint32_t)sub * D * 4;
 
       // ---- pass 1: counts --------------------------------------------------
-      float n1f = 0.0f;
+      float n1p = 0.0f;
       uint32_t mand = 0x01010101u;
-#pragma unroll
-      for (int k = 0; k < NG; ++k) {
-        if (k < kfull) {
-          const float4 x = lds128(xp + LPP * k * 16);
-          n1f += (x.x + x.y) + (x.z + x.w);
-          mand &= lds32(mp + LPP * k * 4);
-        }
+#pragma unroll 4
+      for (int k = 0; k < kfull; ++k) {
+        const float4 x = lds128(xp + LPP * k * 16);
+        n1p += (x.x + x.y) + (x.z + x.w);
+        mand &= lds32(mp + LPP * k * 4);
       }
       if (has_tail) {
         const float4 x = lds128(xp + LPP * kfull * 16);
-        n1f += (x.x + x.y) + (x.z + x.w);
+        n1p += (x.x + x.y) + (x.z + x.w);
         mand &= lds32(mp + LPP * kfull * 4);
       }
       const bool full_obs = __all_sync(0xffffffffu, mand == 0x01010101u);
-      float nobsf = (float)I;
+      int n1 = (int)n1p, nobs = 0;   // 0/1 responses: the float partial sum is an exact small integer
       if (!full_obs) {
-        int n1 = 0, nobs = 0;
+        n1 = 0;
         auto count = [&](int gi) {
           const float4 x = lds128(xp + gi * 16);
           const uint32_t m = lds32(mp + gi * 4);
@@ -287,18 +292,13 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
           n1 += (int)(o0 && x.x > 0.5f) + (int)(o1 && x.y > 0.5f) + (int)(o2 && x.z > 0.5f) +
                 (int)(o3 && x.w > 0.5f);
         };
-#pragma unroll
-        for (int k = 0; k < NG; ++k)
-          if (k < kfull) count(LPP * k);
+#pragma unroll 2
+        for (int k = 0; k < kfull; ++k) count(LPP * k);
         if (has_tail) count(LPP * kfull);
-        n1f = (float)n1;
-        nobsf = (float)nobs;
       }
-#pragma unroll
-      for (int o = LPP / 2; o > 0; o >>= 1) {
-        n1f += __shfl_xor_sync(0xffffffffu, n1f, o);
-        if (!full_obs) nobsf += __shfl_xor_sync(0xffffffffu, nobsf, o);
-      }
+      // integer sub-group sums in one REDUX each
+      const float n1f = (float)__reduce_add_sync(submask, n1);
+      const float nobsf = full_obs ? (float)I : (float)__reduce_add_sync(submask, nobs);
       const float n0f = nobsf - n1f, nmiss = (float)I - nobsf;
 
       // ---- per-person posterior and draw -----------------------------------
@@ -308,10 +308,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
       for (int d = 0; d < D; ++d) {
         const float S = fmaf(n0f, tau[0][d], fmaf(n1f, tau[1][d], nmiss * prior_tau));
         const float N = fmaf(n0f, mt[0][d], n1f * mt[1][d]);
-        invS[d] = __fdividef(1.0f, S);           // = exp(logvar)
+        invS[d] = rcp_approx(S);                 // = exp(logvar)
         amu[d] = N * invS[d];
         alv[d] = -kLn2 * lg2_approx(S);          // log(1 / S)
-        sd[d] = rsqrtf(S);                       // exp(logvar / 2)
+        sd[d] = rsqrt_approx(S);                 // exp(logvar / 2)
         epsv[d] = __uint_as_float(lds32(ep + d * 4));
         th[d] = fmaf(epsv[d], sd[d], amu[d]);
         tsum += th[d];
@@ -393,8 +393,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
         const int g = tt + kF2TeamThreads * k;
         if (g < n_groups) {
           uint32_t a = sb + (uint32_t)g * 16;
-          for (int r = 0; r < rows; ++r, a += (uint32_t)I * 4) {
+          auto add_row = [&](int r) {
             const float4 dz = lds128(a);
+            a += (uint32_t)I * 4;
             const float dzs[4] = {dz.x, dz.y, dz.z, dz.w};
             float thr[D];
 #pragma unroll
@@ -405,6 +406,17 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
               for (int d = 0; d < DA; ++d) acc[(k * 4 + ci) * F + d] = fmaf(dzs[ci], thr[d], acc[(k * 4 + ci) * F + d]);
               acc[(k * 4 + ci) * F + DA] += dzs[ci];
             }
+          };
+          if (rows == R) {  // R is a multiple of 4
+            for (int r = 0; r < R; r += 4) {
+              add_row(r);
+              add_row(r + 1);
+              add_row(r + 2);
+              add_row(r + 3);
+            }
+          } else {
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) add_row(r);
           }
         }
       }
