@@ -6,10 +6,14 @@ reported as person x item cells/s, 2PL synthetic).
     python bench.py --impl reference --steps K --warmup W    # reference CPU arm
 
 One "step" is one pass of the hot path over the whole resident response
-matrix: by default a full training step (zero_grad, fused forward+backward of
-the ELBO, [all-reduce of the loss and parameter gradients at N > 1], Adam) --
-the body of the reference's vibo.py:243-268 -- with the matrix as one batch;
-``--mode eval`` times the forward-only ELBO evaluation instead.
+matrix.  The headline ``value`` follows the metric's definition (SURVEY.md
+8d): one ELBO eval = one fused forward ELBO over the resident matrix, scalar
+out (``--mode eval``, the default; body of the reference's vibo.py:285-312).
+The same JSON line also carries ``train_step``: the full training step
+(zero_grad, fused forward+backward of the ELBO, [all-reduce of the loss and
+parameter gradients at N > 1], Adam) -- the body of vibo.py:243-268 -- timed
+the same way, with its own roofline entry; ``--mode train`` makes that the
+headline instead.
 
 Workload (``--workload``): c4 (default) = 2PL, 1,000,000 x 1,000, ability-dim
 1 -- the configuration BASELINE.json's north-star roofline target is quoted on
@@ -147,16 +151,15 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per launch of the fused kernel from the committed ncu capture."""
+def ncu_traffic(workload, mode):
+    """DRAM bytes (read + write) per launch of the fused kernel, from the ncu
+    --set full capture summarised in profiles/fused_kernel_ncu.json."""
     try:
         with open(os.path.join(ROOT, "profiles", "fused_kernel_ncu.json")) as f:
             rec = json.load(f)
-        if rec.get("workload") == workload:
-            return rec.get("dram_bytes_per_launch")
+        return rec[workload][mode]["dram_bytes_per_launch"]
     except Exception:
-        pass
-    return None
+        return None
 
 
 # --------------------------------------------------------------------------
@@ -214,7 +217,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    ap.add_argument("--mode", default="eval", choices=["train", "eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="capture the step in a CUDA graph (1/0)")
@@ -266,71 +269,79 @@ def main():
                                        person_offset=rank * P, use_kl_divergence=(flows == 0),
                                        cuda_graph=bool(args.cuda_graph))
 
-    def step(i):
-        if args.mode == "train":
-            return trainer.train_step(resp, mask, step_index=i)
-        return trainer.eval_step(resp, mask, step_index=i)
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = lib.vibo_launch_count()
-    lib.vibo_profile_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    ev0.record()
-    for i in range(args.steps):
-        out = step(args.warmup + i)
-    ev1.record()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    if world > 1:
-        dist.barrier()
     import ctypes
-    n_l, tot_ms = ctypes.c_int(0), ctypes.c_double(0.0)
-    lib.vibo_profile_end(ctypes.byref(n_l), ctypes.byref(tot_ms))
-    launches = int(lib.vibo_launch_count() - launches0)
-    if trainer.graph_replays:
-        launches = trainer.kernels_per_step * args.steps
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    loss_val = float(out.item()) if out is not None else None
+    peak, peak_src = measured_peak()
 
-    cells_per_step = P * I * world
-    value = cells_per_step * args.steps / (total_ms * 1e-3)
+    def run(mode, i, eager=False, rows=None):
+        r, m = rows if rows is not None else (resp, mask)
+        if mode == "train":
+            return trainer.train_step(r, m, step_index=i, force_eager=eager)
+        return trainer.eval_step(r, m, step_index=i, force_eager=eager)
 
-    # roofline of the dominant kernel: device time of the fused kernel alone,
-    # bracketed by CUDA events on its launch stream (vibo_profile_*); when the
-    # step is replayed from a CUDA graph the brackets are taken on a separate
-    # un-graphed timing pass of the same step.
-    if n_l.value == 0:
+    def time_mode(mode, sampler=None):
+        """W warm-up steps, then K timed steps bracketed by barrier + synchronize;
+        device time by CUDA events, max over ranks."""
+        for i in range(max(args.warmup, 3)):
+            run(mode, i)
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        replays0 = trainer.graph_replays
+        launches0 = lib.vibo_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        ev0.record()
+        out = None
+        for i in range(args.steps):
+            out = run(mode, args.warmup + i)
+        ev1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        if world > 1:
+            dist.barrier()
+        launches = int(lib.vibo_launch_count() - launches0)
+        graphed = trainer.graph_replays > replays0
+        if graphed:
+            launches = trainer.kernels_per_step * args.steps
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        total_ms = float(ms.item())
+        clocks = sampler.stop(t0, t1) if sampler is not None else None
+        # device time of the dominant kernel alone: CUDA events recorded around
+        # its launch on the launching stream (vibo_profile_*), on an un-graphed
+        # pass of the same step (a graph replay cannot carry the brackets)
+        n_l, tot = ctypes.c_int(0), ctypes.c_double(0.0)
         lib.vibo_profile_begin()
         for i in range(5):
-            trainer.train_step(resp, mask, step_index=1000 + i, force_eager=True) if args.mode == "train" \
-                else trainer.eval_step(resp, mask, step_index=1000 + i, force_eager=True)
+            run(mode, 1000 + i, eager=True)
         torch.cuda.synchronize()
-        lib.vibo_profile_end(ctypes.byref(n_l), ctypes.byref(tot_ms))
-    peak, peak_src = measured_peak()
-    roofline = None
-    if n_l.value > 0:
-        k_ms = tot_ms.value / n_l.value
-        achieved = P * I * BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
-                    "kernel": "fused_uncond_kernel" if trainer.uses_fused else "general kernels",
-                    "kernel_ms": k_ms, "algorithmic_bytes_per_cell": BYTES_PER_CELL,
-                    "peak_source": peak_src}
+        lib.vibo_profile_end(ctypes.byref(n_l), ctypes.byref(tot))
+        roofline = None
+        if n_l.value > 0:
+            k_ms = tot.value / n_l.value
+            achieved = P * I * BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": ncu_traffic(args.workload, mode),
+                        "kernel": ("fused2_kernel<GRAD=%s>" % ("true" if mode == "train" else "false"))
+                        if trainer.uses_fused else "general kernels",
+                        "kernel_ms": k_ms, "algorithmic_bytes_per_cell": BYTES_PER_CELL,
+                        "peak_source": peak_src}
+        return {"value": P * I * world * args.steps / (total_ms * 1e-3), "unit": "cells/s",
+                "ms_per_step": total_ms / args.steps, "evals_per_sec": args.steps / (total_ms * 1e-3),
+                "loss": float(out.item()), "gpu_launches": launches, "cuda_graph": graphed,
+                "roofline": roofline, "clocks": clocks}
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    main_res = time_mode(args.mode, sampler)
+    other_mode = "train" if args.mode == "eval" else "eval"
+    other_res = time_mode(other_mode)
+    total_ms = main_res["ms_per_step"] * args.steps
+    value = main_res["value"]
 
     # end-to-end through the public API with HOST (pinned) rows: H2D of the
     # step's rows and D2H of the loss inside the timed region.
@@ -340,8 +351,7 @@ def main():
         resp_h = resp[:Pe].cpu().pin_memory()
         mask_h = mask[:Pe].cpu().pin_memory()
         for i in range(2):
-            trainer.train_step(resp_h, mask_h, step_index=i) if args.mode == "train" else \
-                trainer.eval_step(resp_h, mask_h, step_index=i)
+            run(args.mode, i, rows=(resp_h, mask_h))
         torch.cuda.synchronize()
         ksteps = max(3, min(args.steps, 10))
         if world > 1:
@@ -349,8 +359,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(ksteps):
-            o = trainer.train_step(resp_h, mask_h, step_index=i) if args.mode == "train" else \
-                trainer.eval_step(resp_h, mask_h, step_index=i)
+            o = run(args.mode, i, rows=(resp_h, mask_h))
             _ = o.item()
         e1.record()
         torch.cuda.synchronize()
@@ -371,19 +380,24 @@ def main():
                         "sample": r["sample"]}
 
     if rank == 0:
+        other_res.pop("clocks", None)
         line = {"metric": metric, "value": value, "unit": "cells/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": describe(args.workload), "mode": args.mode,
+                           "step": "one fused forward ELBO over the resident matrix (scalar out)"
+                           if args.mode == "eval" else
+                           "zero_grad + fused ELBO forward/backward + all-reduce + Adam",
                            "rows_per_gpu": P, "items": I,
                            "l2": "inputs (%.2f GB/GPU) >> 126 MB L2, no flush" % (P * I * 5 / 1e9)
                            if P * I * 5 > 4 * 126e6 else "inputs fit L2; no flush (small parity config)",
                            "parallelism": f"person-sharded dp{world}",
-                           "cuda_graph": bool(trainer.graph_replays)},
-                "evals_per_sec": args.steps / (total_ms * 1e-3), "loss": loss_val,
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "e2e": e2e, "clocks": clocks}
+                           "cuda_graph": main_res["cuda_graph"]},
+                "evals_per_sec": main_res["evals_per_sec"], "loss": main_res["loss"],
+                "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
+                "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": main_res["clocks"],
+                ("train_step" if other_mode == "train" else "eval_step"): other_res}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

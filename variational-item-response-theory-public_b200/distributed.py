@@ -86,9 +86,15 @@ class ShardedElboTrainer:
         return self.flat[0]
 
     def _graphed(self, kind, body, response, mask):
+        """Capture the whole single-GPU step (small PyTorch ops, the fused kernel
+        and Adam) in one CUDA graph keyed by the row buffers; noise
+        comes from torch's graph-safe Philox generator so every replay draws
+        fresh eps.  Falls back to eager launches if capture is refused."""
         from . import _lib
         key = (kind, response.data_ptr(), mask.data_ptr(), tuple(response.shape))
         g = self._graphs.get(key)
+        if g is False:
+            return None
         if g is None:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -100,8 +106,15 @@ class ShardedElboTrainer:
             lib = _lib.load()
             n0 = lib.vibo_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                body(response, mask, None)   # seed=None: noise from torch's graph-safe generator
+            try:
+                with torch.cuda.graph(g):
+                    body(response, mask, None)   # seed=None: noise from torch's graph-safe generator
+            except Exception as exc:  # e.g. a collective that cannot be captured
+                import warnings
+                warnings.warn(f"CUDA graph capture of the {kind} step failed ({exc}); running eagerly")
+                torch.cuda.synchronize()
+                self._graphs[key] = False
+                return None
             self.kernels_per_step = int(lib.vibo_launch_count() - n0)
             self._graphs[key] = g
         g.replay()
@@ -113,12 +126,17 @@ class ShardedElboTrainer:
         """Returns the (all-reduced) loss as a 0-d tensor view (read it before
         the next step)."""
         self.model.train()
+        # (NCCL collectives are kept out of graph capture: capturing them hung on this stack)
         if self.cuda_graph and response.is_cuda and not force_eager and self.world_size == 1:
-            return self._graphed("train", self._train_body, response, mask)
+            out = self._graphed("train", self._train_body, response, mask)
+            if out is not None:
+                return out
         return self._train_body(response, mask, self.seed + step_index)
 
     def eval_step(self, response, mask, step_index=0, force_eager=False):
         self.model.eval()
         if self.cuda_graph and response.is_cuda and not force_eager and self.world_size == 1:
-            return self._graphed("eval", self._eval_body, response, mask)
+            out = self._graphed("eval", self._eval_body, response, mask)
+            if out is not None:
+                return out
         return self._eval_body(response, mask, self.seed + step_index)

@@ -59,6 +59,8 @@ class AbilityInferenceNetwork(nn.Module):
         self.ability_merge = ability_merge
         self.replace_missing_with_prior = replace_missing_with_prior
         self.mlp = _encoder_mlp(response_dim, hidden_dim, ability_dim * 2)
+        # the two possible cell inputs; non-persistent so state_dict keys stay the reference's
+        self.register_buffer("_cell_inputs", torch.tensor([[0.0], [1.0]]), persistent=False)
 
     @property
     def missing_policy(self):
@@ -66,9 +68,7 @@ class AbilityInferenceNetwork(nn.Module):
 
     def expert_table(self, item_feat=None):
         """(2, 1, 2D): the MLP on the two possible cell inputs r = 0, 1."""
-        w = self.mlp[0].weight
-        rows = torch.tensor([[0.0], [1.0]], dtype=w.dtype, device=w.device)
-        return self.mlp(rows).unsqueeze(1)
+        return self.mlp(self._cell_inputs.to(self.mlp[0].weight.dtype)).unsqueeze(1)
 
     def forward(self, response, mask, item_feat=None):
         resp, msk = VF.prepare_rows(response, mask)
@@ -96,8 +96,7 @@ class ConditionalAbilityInferenceNetwork(AbilityInferenceNetwork):
     def expert_table(self, item_feat=None):
         """(2, I, 2D): the MLP on [r, item_feat_j] for r = 0, 1 and every item."""
         I = item_feat.shape[0]
-        r = torch.zeros(2, I, 1, dtype=item_feat.dtype, device=item_feat.device)
-        r[1] = 1.0
+        r = self._cell_inputs.to(item_feat.dtype).view(2, 1, 1).expand(2, I, 1)
         rows = torch.cat([r, item_feat.unsqueeze(0).expand(2, I, -1)], dim=2)
         return self.mlp(rows.reshape(2 * I, -1)).reshape(2, I, -1)
 
