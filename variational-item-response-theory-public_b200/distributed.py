@@ -67,40 +67,46 @@ class ShardedElboTrainer:
                                      person_offset=self.person_offset,
                                      item_term_scale=1.0 / self.world_size)
 
-    def _train_body(self, response, mask, seed):
+    def _train_pre(self, response, mask, seed):
         self.flat.zero_()
         loss = self._loss(response, mask, seed)
         loss.backward()
         self.flat[0:1].copy_(loss.detach().reshape(1))
+
+    def _eval_pre(self, response, mask, seed):
+        with torch.no_grad():
+            loss = self._loss(response, mask, seed)
+            self.flat[0:1].copy_(loss.reshape(1))
+
+    def _train_body(self, response, mask, seed):
+        self._train_pre(response, mask, seed)
         if self.world_size > 1:
             dist.all_reduce(self.flat, group=self.group)
         self.opt.step()
         return self.flat[0]
 
     def _eval_body(self, response, mask, seed):
-        with torch.no_grad():
-            loss = self._loss(response, mask, seed)
-            self.flat[0:1].copy_(loss.reshape(1))
-            if self.world_size > 1:
-                dist.all_reduce(self.flat[0:1], group=self.group)
+        self._eval_pre(response, mask, seed)
+        if self.world_size > 1:
+            dist.all_reduce(self.flat[0:1], group=self.group)
         return self.flat[0]
 
-    def _graphed(self, kind, body, response, mask):
-        """Capture the whole single-GPU step (small PyTorch ops, the fused kernel
-        and Adam) in one CUDA graph keyed by the row buffers; noise
-        comes from torch's graph-safe Philox generator so every replay draws
-        fresh eps.  Falls back to eager launches if capture is refused."""
+    def _replay(self, key, fn, count_kernels=False):
+        """Capture `fn()` in a CUDA graph on first use (after eager warm-up on a
+        side stream), then replay it.  The NCCL all-reduce is deliberately NOT
+        captured (capturing it hung on this stack): a training step is
+        graph(pre) -> all_reduce -> graph(Adam).  Returns False if capture was
+        refused, after which the caller runs eagerly."""
         from . import _lib
-        key = (kind, response.data_ptr(), mask.data_ptr(), tuple(response.shape))
         g = self._graphs.get(key)
         if g is False:
-            return None
+            return False
         if g is None:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    body(response, mask, None)
+                    fn()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             lib = _lib.load()
@@ -108,35 +114,44 @@ class ShardedElboTrainer:
             g = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(g):
-                    body(response, mask, None)   # seed=None: noise from torch's graph-safe generator
-            except Exception as exc:  # e.g. a collective that cannot be captured
+                    fn()
+            except Exception as exc:
                 import warnings
-                warnings.warn(f"CUDA graph capture of the {kind} step failed ({exc}); running eagerly")
+                warnings.warn(f"CUDA graph capture of {key[0]} failed ({exc}); running eagerly")
                 torch.cuda.synchronize()
                 self._graphs[key] = False
-                return None
-            self.kernels_per_step = int(lib.vibo_launch_count() - n0)
+                return False
+            if count_kernels:
+                self.kernels_per_step = int(lib.vibo_launch_count() - n0)
             self._graphs[key] = g
         g.replay()
-        self.graph_replays += 1
-        return self.flat[0]
+        return True
 
     # ------------------------------------------------------------------ steps
     def train_step(self, response, mask, step_index=0, force_eager=False):
         """Returns the (all-reduced) loss as a 0-d tensor view (read it before
-        the next step)."""
+        the next step).  Graph replays draw noise from torch's graph-safe
+        generator (seed=None); eager steps key the in-kernel Philox by
+        ``seed + step_index``."""
         self.model.train()
-        # (NCCL collectives are kept out of graph capture: capturing them hung on this stack)
-        if self.cuda_graph and response.is_cuda and not force_eager and self.world_size == 1:
-            out = self._graphed("train", self._train_body, response, mask)
-            if out is not None:
-                return out
+        if self.cuda_graph and response.is_cuda and not force_eager:
+            key = (response.data_ptr(), mask.data_ptr(), tuple(response.shape))
+            if self._replay(("train_pre",) + key, lambda: self._train_pre(response, mask, None), True):
+                if self.world_size > 1:
+                    dist.all_reduce(self.flat, group=self.group)
+                if not self._replay(("train_post",), self.opt.step):
+                    self.opt.step()
+                self.graph_replays += 1
+                return self.flat[0]
         return self._train_body(response, mask, self.seed + step_index)
 
     def eval_step(self, response, mask, step_index=0, force_eager=False):
         self.model.eval()
-        if self.cuda_graph and response.is_cuda and not force_eager and self.world_size == 1:
-            out = self._graphed("eval", self._eval_body, response, mask)
-            if out is not None:
-                return out
+        if self.cuda_graph and response.is_cuda and not force_eager:
+            key = (response.data_ptr(), mask.data_ptr(), tuple(response.shape))
+            if self._replay(("eval_pre",) + key, lambda: self._eval_pre(response, mask, None), True):
+                if self.world_size > 1:
+                    dist.all_reduce(self.flat[0:1], group=self.group)
+                self.graph_replays += 1
+                return self.flat[0]
         return self._eval_body(response, mask, self.seed + step_index)
