@@ -213,6 +213,25 @@ def run_log_marginal(models):
     return rec
 
 
+def run_mask_fixture():
+    """artificially_mask_dataset of the reference (src/datasets.py:46-78) on a toy
+    dataset object; nltk is a dead import there (datasets.py:8) and is stubbed."""
+    import types
+    sys.modules.setdefault("nltk", types.SimpleNamespace(word_tokenize=None))
+    from src import datasets as ref_ds
+    rng = np.random.RandomState(3)
+    P, I = 23, 11
+    response = (rng.rand(P, I, 1) < 0.5).astype(np.float32)
+    mask = np.ones((P, I, 1), dtype=np.float32)
+    holes = rng.rand(P, I) < 0.1
+    response[holes] = -1
+    mask[holes] = 0
+    ds = types.SimpleNamespace(response=response.copy(), mask=mask.copy())
+    out = ref_ds.artificially_mask_dataset(ds, 0.2)
+    return dict(response_in=response, mask_in=mask, response_out=out.response, mask_out=out.mask,
+                missing_indices=out.missing_indices, missing_labels=out.missing_labels)
+
+
 def main():
     models = _import_reference()
     index = []
@@ -222,6 +241,7 @@ def main():
         index.append(c)
         print(f"{c['name']:40s} loss={float(rec['loss']):.6f}")
     np.savez_compressed(os.path.join(HERE, "log_marginal_2pl_d2.npz"), **run_log_marginal(models))
+    np.savez_compressed(os.path.join(HERE, "artificial_mask.npz"), **run_mask_fixture())
     with open(os.path.join(HERE, "index.json"), "w") as f:
         json.dump(dict(torch=torch.__version__, reference=REF, cases=index), f, indent=1)
 

@@ -87,43 +87,68 @@ __global__ void philox_fill_kernel(int64_t P, int D, int64_t person_offset, uint
 
 // Sum the per-CTA partials in a fixed order; apply the expert chain rule and
 // the sign convention g = d loss_k / d (.) with loss_k = -LL + ...
-__global__ void fused_finalize_kernel(int nparts, int I, int F, int DA, int D, bool grad, bool accumulate,
-                                      const double* __restrict__ part_scalar,
-                                      const float* __restrict__ part_table,
-                                      const float* __restrict__ part_item, const float* __restrict__ table,
-                                      double* __restrict__ out_scalars, float* __restrict__ g_table,
-                                      float* __restrict__ g_item) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (grad) {
-    for (int k = tid; k < I * F; k += gridDim.x * blockDim.x) {
-      double s = 0.0;
-      for (int p = 0; p < nparts; ++p) s += part_item[(size_t)p * I * F + k];
+// Block = 32 outputs x 8 partial-slices: each thread sums every 8th partial
+// (short dependent chains), then the 8 slices are combined through shared
+// memory in a fixed order, so the result is deterministic.
+constexpr int kFinSlices = 8;
+__global__ void __launch_bounds__(32 * kFinSlices)
+fused_finalize_kernel(int nparts, int I, int F, int DA, int D, bool grad, bool accumulate,
+                      const double* __restrict__ part_scalar, const float* __restrict__ part_table,
+                      const float* __restrict__ part_item, const float* __restrict__ table,
+                      double* __restrict__ out_scalars, float* __restrict__ g_table,
+                      float* __restrict__ g_item) {
+  __shared__ double s_red[kFinSlices][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n_item = grad ? I * F : 0;
+  // blocks [0, ceil(n_item/32)) : item gradients; last block: scalars + table gradients
+  const int item_blocks = (n_item + 31) / 32;
+  if ((int)blockIdx.x < item_blocks) {
+    const int k = blockIdx.x * 32 + lane;
+    double s = 0.0;
+    if (k < n_item)
+      for (int p = slice; p < nparts; p += kFinSlices) s += part_item[(size_t)p * n_item + k];
+    s_red[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && k < n_item) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < kFinSlices; ++q) t += s_red[q][lane];
       const int f = k % F;
-      const float v = (float)(f < DA ? s : -s);  // acc_a holds +sum dz*theta, the others sum dz
+      const float v = (float)(f < DA ? t : -t);  // acc_a holds +sum dz*theta, the others sum dz
       g_item[k] = accumulate ? g_item[k] + v : v;
     }
+    return;
   }
-  if (blockIdx.x == 0) {
-    if (threadIdx.x < 2) {
-      double s = 0.0;
-      for (int p = 0; p < nparts; ++p) s += part_scalar[(size_t)p * 2 + threadIdx.x];
-      out_scalars[threadIdx.x] = accumulate ? out_scalars[threadIdx.x] + s : s;
-    }
-    if (grad && threadIdx.x >= 32 && threadIdx.x < 32 + 2 * D) {
-      const int r = (threadIdx.x - 32) / D, d = (threadIdx.x - 32) % D;
-      double A = 0.0, B = 0.0;
-      for (int p = 0; p < nparts; ++p) {
-        A += part_table[(size_t)p * 4 * D + r * D + d];
-        B += part_table[(size_t)p * 4 * D + 2 * D + r * D + d];
-      }
-      const float mu = table[r * 2 * D + d], lam = table[r * 2 * D + D + d];
-      const float el = expf(lam);
-      const float tau = 1.0f / (el + kPoeEps);
-      const float gm = tau * (float)A;
-      const float gl = (mu * (float)A + (float)B) * (-el * tau * tau);
-      g_table[r * 2 * D + d] = accumulate ? g_table[r * 2 * D + d] + gm : gm;
-      g_table[r * 2 * D + D + d] = accumulate ? g_table[r * 2 * D + D + d] + gl : gl;
-    }
+  // lanes 0..1: LL / person term; lanes 2..2+4D: A0 A1 B0 B1 sums of the expert table
+  const int nq = 2 + (grad ? 4 * D : 0);
+  double s = 0.0;
+  if (lane < nq) {
+    for (int p = slice; p < nparts; p += kFinSlices)
+      s += lane < 2 ? part_scalar[(size_t)p * 2 + lane] : (double)part_table[(size_t)p * 4 * D + (lane - 2)];
+  }
+  s_red[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < kFinSlices; ++q) t += s_red[q][lane];
+    s_red[0][lane] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const double t = s_red[0][threadIdx.x];
+    out_scalars[threadIdx.x] = accumulate ? out_scalars[threadIdx.x] + t : t;
+  }
+  if (grad && threadIdx.x >= 32 && (int)threadIdx.x < 32 + 2 * D) {
+    const int r = (threadIdx.x - 32) / D, d = (threadIdx.x - 32) % D;
+    const float A = (float)s_red[0][2 + r * D + d], B = (float)s_red[0][2 + 2 * D + r * D + d];
+    const float mu = table[r * 2 * D + d], lam = table[r * 2 * D + D + d];
+    const float el = expf(lam);
+    const float tau = 1.0f / (el + kPoeEps);
+    const float gm = tau * A;
+    const float gl = (mu * A + B) * (-el * tau * tau);
+    g_table[r * 2 * D + d] = accumulate ? g_table[r * 2 * D + d] + gm : gm;
+    g_table[r * 2 * D + D + d] = accumulate ? g_table[r * 2 * D + D + d] + gl : gl;
   }
 }
 
@@ -234,11 +259,10 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   if (e != cudaSuccess) return e;
   note_launch(2);
   const int DA = d.irt_model == 1 ? 0 : D;
-  const int n = d.num_item * F;
-  int fb = (n + 127) / 128;
-  if (fb < 1) fb = 1;
-  fused_finalize_kernel<<<fb, 128, 0, st>>>(pl.grid, d.num_item, F, DA, D, grad, accumulate, part_scalar,
-                                            part_table, part_item, table, out_scalars, g_table, g_item);
+  const int fb = (grad ? (d.num_item * F + 31) / 32 : 0) + 1;
+  fused_finalize_kernel<<<fb, 32 * kFinSlices, 0, st>>>(pl.grid, d.num_item, F, DA, D, grad, accumulate,
+                                                        part_scalar, part_table, part_item, table,
+                                                        out_scalars, g_table, g_item);
   return cudaGetLastError();
 }
 
