@@ -79,23 +79,20 @@ __device__ __forceinline__ void f2_group(uint32_t xaddr, uint32_t m4, const floa
 #pragma unroll
       for (int d = 0; d < DA; ++d) z = fmaf(-th[d], av[d], z);
     }
-    float xm = xs[c] - 0.5f;
+    // ll = x zc - softplus(zc) = (x - 1) zc - log(1 + E),  E = exp(-zc);  d ll / d z = x - 1/(1 + E)
+    float x = xs[c];
     if (!FULL) {
       const bool o = ((m4 >> (8 * c)) & 0xffu) != 0;
-      xm = o ? xm : 0.0f;   // missing cell -> neutral cell (x = 1/2, z = 0)
+      x = o ? x : 0.5f;   // missing cell -> neutral cell (x = 1/2, z = 0): gradient 0, ll = -log 2
       z = o ? z : 0.0f;
     }
     const float zc = EXACT ? fminf(fmaxf(z, -kLogitClamp), kLogitClamp) : z;
-    const float e = ex2_approx(fabsf(zc) * kNegLog2e);
-    const float w = 1.0f + e;
-    s1 = fmaf(xm, zc, s1);
-    s2 += fabsf(zc);
+    const float w = 1.0f + ex2_approx(zc * kNegLog2e);
+    s1 = fmaf(x - 1.0f, zc, s1);
     s3 += lg2_approx(w);
     float dz = 0.0f;
     if (GRAD) {
-      const float h = rcp_approx(w) - 0.5f;  // sigmoid(|zc|) - 1/2
-      const float cs = __uint_as_float((__float_as_uint(h) & 0x7fffffffu) | (__float_as_uint(zc) & 0x80000000u));
-      dz = xm - cs;                           // x - sigmoid(zc)
+      dz = x - rcp_approx(w);                  // x - sigmoid(zc)
       if (EXACT) dz = (z == zc) ? dz : 0.0f;  // zero gradient outside the eps32 clamp
       if (MODEL == 1) {
         gth[0] -= dz;
@@ -247,14 +244,17 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
                  step_e = (uint32_t)TW * PPW * D * 4;
   int s = 0;
   uint32_t phase = 0;
-  int64_t rows_left = p.P - chunk0 * R;
-  const int64_t rows_step = chunk_step * R;
+  // 32-bit loop state: this team runs n_it stages; only the globally last chunk can be ragged
+  const int n_it = chunk0 < n_chunks ? (int)((n_chunks - chunk0 + chunk_step - 1) / chunk_step) : 0;
+  const int last_rows = (int)(p.P - (n_chunks - 1) * R);
+  const bool owns_last = n_it > 0 && chunk0 + (int64_t)(n_it - 1) * chunk_step == n_chunks - 1;
+  const uint32_t stage_bytes = (uint32_t)L.stage_bytes;
 
-  for (int64_t c = chunk0; c < n_chunks; c += chunk_step, rows_left -= rows_step) {
+  for (int it = 0; it < n_it; ++it) {
     mbar_wait_addr(bar0 + (uint32_t)s * 8, phase);
-    const uint32_t sb = stage0 + (uint32_t)s * (uint32_t)L.stage_bytes;
+    const uint32_t sb = stage0 + (uint32_t)s * stage_bytes;
     const uint32_t thb = theta0 + (uint32_t)s * (kF2MaxRows * D * 4);  // this slot's theta rows
-    const int rows = rows_left < R ? (int)rows_left : R;
+    const int rows = (owns_last && it == n_it - 1) ? last_rows : R;
 
     // ======================= phase A: one sub-group per row =================
     uint32_t xrow = sb + off_x, mrow = sb + off_m, erow = sb + off_e;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
           if (GRAD) asm volatile("st.shared.f32 [%0], %1;" ::"r"(thb + (uint32_t)(r * D + d) * 4), "f"(th[d]) : "memory");
         }
         if (p.out_mu != nullptr) {
-          const int64_t row = c * R + r;
+          const int64_t row = (chunk0 + (int64_t)it * chunk_step) * R + r;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
             p.out_mu[row * D + d] = amu[d];
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
           f2_pass2<MODEL, D, LPP, NG, GRAD, true, true>(xp, mp, pp, n_groups, kfull, has_tail, th, tsum, gth, s1, s2, s3);
         else
           f2_pass2<MODEL, D, LPP, NG, GRAD, false, true>(xp, mp, pp, n_groups, kfull, has_tail, th, tsum, gth, s1, s2, s3);
-        ll_acc += s1 - 0.5f * s2 - kLn2 * s3;
+        ll_acc += s1 - kLn2 * s3;   // s2 unused in this formulation
       }
 
       // ---- per-person backward ---------------------------------------------
@@ -431,9 +431,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
       if (last) atomicExch(&t_done[s], 0);
     }
     last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-      const int64_t cn = c + (int64_t)NS * chunk_step;
-      if (cn < n_chunks) fused_issue_chunk<D>(p, L, cn, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
+    if (last && it + NS < n_it) {
+      const int64_t cn = chunk0 + (int64_t)(it + NS) * chunk_step;
+      fused_issue_chunk<D>(p, L, cn, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
     }
     if (++s == NS) {
       s = 0;
