@@ -166,6 +166,36 @@ int vibo_bernoulli_loglik(const vibo_desc* desc, const float* response, const ui
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Parameter-side chain of the UNCONDITIONAL model (conditional == 0), i.e. the
+ * tiny tensors around the row kernels, as two launches:
+ *
+ *   forward   item_feat (I, F) = mu_lookup + exp(logvar_lookup / 2) * eps_item
+ *                                             [models.py:359-361, :506-510]
+ *             table (2, 1, 2D) = ability_encoder.mlp on the two possible cell
+ *                                inputs 0 and 1   [models.py:575-582, :599]
+ *             item_term (double[1]) = KL(q(item) || N(0,1))  [utils.py:85-88]
+ *                  (VIBO_ELBO_KL) or -(log p(item) - log q(item)) [utils.py:59-67]
+ *             hidden (2, 2, H): activations kept for the backward.
+ *   backward  gradients of every parameter given g_table = d loss / d table,
+ *             g_item = d loss / d item_feat (both from vibo_fused_elbo) and
+ *             g_item_term = d loss / d item_term (device float[1]).
+ *
+ * w0 (H, 1), b0 (H), w2 (H, H), b2 (H), w4 (2D, H), b4 (2D) are the
+ * ability_encoder.mlp.{0,2,4}.{weight,bias} tensors; hidden_dim <= 256.
+ */
+int vibo_param_forward(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
+                       const float* logvar_lookup, const float* eps_item, const float* w0,
+                       const float* b0, const float* w2, const float* b2, const float* w4,
+                       const float* b4, float* item_feat, float* table, float* hidden,
+                       double* item_term, void* stream);
+int vibo_param_backward(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
+                        const float* logvar_lookup, const float* eps_item, const float* w2,
+                        const float* w4, const float* hidden, const float* g_table,
+                        const float* g_item, const float* g_item_term, float* g_mu_lookup,
+                        float* g_logvar_lookup, float* g_w0, float* g_b0, float* g_w2, float* g_b2,
+                        float* g_w4, float* g_b4, void* stream);
+
+/*
  * Measurement hooks (used by bench.py; no effect on results).
  *   vibo_launch_count      kernels this library has launched in this process.
  *   vibo_profile_begin     start bracketing every launch of the fused kernel

@@ -179,6 +179,31 @@ def test_general_kernels_vs_oracle(vb, P, I, D, irt, cond, missing):
     assert rel_l2(g_p.cpu().numpy(), ref_gp) < 1e-5
 
 
+@pytest.mark.parametrize("irt,D,use_kl", [(2, 1, True), (1, 2, True), (3, 3, False), (2, 2, False)])
+def test_param_chain_kernels_match_autograd(vb, irt, D, use_kl):
+    """vibo_param_forward/backward (two kernels) vs the same chain in PyTorch autograd."""
+    P, I = 300, 52
+    cls = {1: vb.VIBO_1PL, 2: vb.VIBO_2PL, 3: vb.VIBO_3PL}[irt]
+    torch.manual_seed(3)
+    model = cls(D, I, ability_merge="product").cuda()
+    g = torch.Generator().manual_seed(4)
+    resp = (torch.rand(P, I, 1, generator=g) < 0.5).float().cuda()
+    mask = (torch.rand(P, I, 1, generator=g) >= 0.1).cuda()
+    eps_item = torch.randn(I, model.item_feat_dim, generator=g).cuda()
+    eps_ab = torch.randn(P, D, generator=g).cuda()
+    out = {}
+    for fused in (True, False):
+        model.fuse_param_chain = fused
+        model.zero_grad()
+        loss = model.fused_elbo(resp, mask, annealing_factor=0.7, use_kl_divergence=use_kl, eps_item=eps_item,
+                                eps_ability=eps_ab, item_term_scale=0.5)
+        loss.backward()
+        out[fused] = (loss.item(), {k: p.grad.clone() for k, p in model.named_parameters()})
+    assert abs(out[True][0] - out[False][0]) <= 1e-6 * abs(out[False][0])
+    for k, gref in out[False][1].items():
+        assert rel_l2(out[True][1][k].cpu().numpy(), gref.cpu().numpy()) < 1e-5, k
+
+
 def test_saturated_cells(vb):
     """|z| beyond the eps32 clamp: value floors at log(eps32), gradient is zero."""
     resp = np.array([[1.0, 0.0, 1.0, 0.0]], dtype=np.float32)

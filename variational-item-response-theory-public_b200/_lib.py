@@ -49,6 +49,8 @@ SIGNATURES = {
     "vibo_link_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_decode": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_bernoulli_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "vibo_param_forward": (C.c_int, [_PD, C.c_int] + [_p] * 14),
+    "vibo_param_backward": (C.c_int, [_PD, C.c_int] + [_p] * 18),
     "vibo_single_pass": (C.c_int, [_PD]),
     "vibo_launch_count": (C.c_uint64, []),
     "vibo_profile_begin": (C.c_int, []),

@@ -290,4 +290,44 @@ int vibo_bernoulli_loglik(const vibo_desc* desc, const float* response, const ui
   return VIBO_OK;
 }
 
+int vibo_param_forward(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
+                       const float* logvar_lookup, const float* eps_item, const float* w0,
+                       const float* b0, const float* w2, const float* b2, const float* w4,
+                       const float* b4, float* item_feat, float* table, float* hidden,
+                       double* item_term, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (desc->conditional) return fail(VIBO_ERR_UNSUPPORTED, "vibo_param_forward covers the unconditional encoder only");
+  if (hidden_dim < 1 || hidden_dim > 256) return fail(VIBO_ERR_UNSUPPORTED, "hidden_dim must be in 1..256");
+  if (!mu_lookup || !logvar_lookup || !eps_item || !w0 || !b0 || !w2 || !b2 || !w4 || !b4 || !item_feat ||
+      !table || !hidden || !item_term)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  const int F = vibo::item_width_host(desc->irt_model, desc->ability_dim);
+  VIBO_CUDA(vibo::launch_param_forward(desc->num_item, F, desc->ability_dim, hidden_dim, desc->elbo_form,
+                                       mu_lookup, logvar_lookup, eps_item, w0, b0, w2, b2, w4, b4, item_feat,
+                                       table, hidden, item_term, static_cast<cudaStream_t>(stream)),
+            "param_forward");
+  return VIBO_OK;
+}
+
+int vibo_param_backward(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
+                        const float* logvar_lookup, const float* eps_item, const float* w2,
+                        const float* w4, const float* hidden, const float* g_table,
+                        const float* g_item, const float* g_item_term, float* g_mu_lookup,
+                        float* g_logvar_lookup, float* g_w0, float* g_b0, float* g_w2, float* g_b2,
+                        float* g_w4, float* g_b4, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (desc->conditional) return fail(VIBO_ERR_UNSUPPORTED, "vibo_param_backward covers the unconditional encoder only");
+  if (hidden_dim < 1 || hidden_dim > 256) return fail(VIBO_ERR_UNSUPPORTED, "hidden_dim must be in 1..256");
+  if (!mu_lookup || !logvar_lookup || !eps_item || !w2 || !w4 || !hidden || !g_table || !g_item ||
+      !g_item_term || !g_mu_lookup || !g_logvar_lookup || !g_w0 || !g_b0 || !g_w2 || !g_b2 || !g_w4 || !g_b4)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  const int F = vibo::item_width_host(desc->irt_model, desc->ability_dim);
+  VIBO_CUDA(vibo::launch_param_backward(desc->num_item, F, desc->ability_dim, hidden_dim, desc->elbo_form,
+                                        mu_lookup, logvar_lookup, eps_item, w2, w4, hidden, g_table, g_item,
+                                        g_item_term, g_mu_lookup, g_logvar_lookup, g_w0, g_b0, g_w2, g_b2,
+                                        g_w4, g_b4, static_cast<cudaStream_t>(stream)),
+            "param_backward");
+  return VIBO_OK;
+}
+
 }  // extern "C"

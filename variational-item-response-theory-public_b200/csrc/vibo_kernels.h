@@ -48,6 +48,17 @@ cudaError_t launch_negate(float* v, int n, cudaStream_t st);
 cudaError_t launch_accumulate(float* dst, const float* src, int n, double* dst2, const double* src2,
                               int n2, cudaStream_t st);
 
+// vibo_param.cu: parameter-side chain of the unconditional model
+cudaError_t launch_param_forward(int I, int F, int D, int H, int form, const float* mu, const float* lv,
+                                 const float* eps, const float* w0, const float* b0, const float* w2,
+                                 const float* b2, const float* w4, const float* b4, float* item_feat,
+                                 float* table, float* hidden, double* item_term, cudaStream_t st);
+cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const float* mu, const float* lv,
+                                  const float* eps, const float* w2, const float* w4, const float* hidden,
+                                  const float* g_table, const float* g_item, const float* g_term,
+                                  float* g_mu, float* g_lv, float* g_w0, float* g_b0, float* g_w2,
+                                  float* g_b2, float* g_w4, float* g_b4, cudaStream_t st);
+
 // vibo_fused.cu: single-pass kernel.  Returns false when the configuration is
 // not covered (caller composes the general kernels instead).
 void profile_begin();

@@ -46,7 +46,9 @@ class ShardedElboTrainer:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         on_gpu = dev.type == "cuda"
-        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=on_gpu, foreach=True)
+        # one fused multi-tensor Adam kernel on the GPU (graph-capturable); plain Adam on CPU (tests)
+        self.opt = torch.optim.Adam(self.params, lr=lr, capturable=True, fused=True) if on_gpu \
+            else torch.optim.Adam(self.params, lr=lr, foreach=True)
         self.cuda_graph = bool(cuda_graph) and on_gpu
         self._graphs = {}
         self.graph_replays = 0

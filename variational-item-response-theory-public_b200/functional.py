@@ -99,6 +99,37 @@ class FusedElboHost(torch.autograd.Function):
         return None, None, g_loss * g_table, g_loss * g_item, None, None
 
 
+class ParamChain(torch.autograd.Function):
+    """Parameter-side chain of the unconditional model in two kernels
+    (vibo_param_forward / vibo_param_backward): item reparameterisation,
+    expert table = encoder MLP on the cell inputs {0, 1}, and the item-side
+    prior term.  Replaces ~80 tiny PyTorch kernels per training step."""
+
+    @staticmethod
+    def forward(ctx, mu, lv, w0, b0, w2, b2, w4, b4, eps_item, irt_model, elbo_form):
+        args = [t.detach().contiguous() for t in (mu, lv, eps_item, w0, b0, w2, b2, w4, b4)]
+        item_feat, table, hidden, term = K.param_forward(*args, irt_model=irt_model, elbo_form=elbo_form)
+        ctx.save_for_backward(args[0], args[1], args[2], args[5], args[7], hidden)
+        ctx.cfg = (irt_model, elbo_form)
+        return item_feat, table, term[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g_item_feat, g_table, g_term):
+        mu, lv, eps_item, w2, w4, hidden = ctx.saved_tensors
+        irt_model, elbo_form = ctx.cfg
+        if g_item_feat is None:
+            g_item_feat = torch.zeros_like(mu)
+        if g_table is None:
+            g_table = torch.zeros(2, 1, w4.shape[0], device=mu.device)
+        if g_term is None:
+            g_term = torch.zeros((), device=mu.device)
+        grads = K.param_backward(mu, lv, eps_item, w2, w4, hidden, g_table.contiguous().float(),
+                                 g_item_feat.contiguous().float(), g_term.reshape(1).float().contiguous(),
+                                 irt_model=irt_model, elbo_form=elbo_form)
+        g_mu, g_lv, g_w0, g_b0, g_w2, g_b2, g_w4, g_b4 = grads
+        return g_mu, g_lv, g_w0, g_b0, g_w2, g_b2, g_w4, g_b4, None, None, None
+
+
 class EncodePosterior(torch.autograd.Function):
     """(ability_mu, ability_logvar) = PoE over each person's experts
     (vibo_encode / vibo_encode_backward)."""

@@ -199,3 +199,39 @@ def bernoulli_loglik(response, mask, response_mu, *, want_grad=True):
                                            _stream(response.device))
     _lib.check(rc, "vibo_bernoulli_loglik")
     return ll, g
+
+
+def param_forward(mu, lv, eps_item, w0, b0, w2, b2, w4, b4, *, irt_model, elbo_form=ELBO_KL):
+    """vibo_param_forward -> (item_feat (I,F), table (2,1,2D), hidden (2,2,H), item_term (1,) f64)."""
+    if not mu.is_cuda:
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    I, F = mu.shape
+    H = w2.shape[0]
+    D = w4.shape[0] // 2
+    desc = make_desc(0, I, D, irt_model, 0, MISSING_PRIOR, elbo_form)
+    item_feat = torch.empty_like(mu)
+    table = torch.empty(2, 1, 2 * D, dtype=torch.float32, device=mu.device)
+    hidden = torch.empty(2, 2, H, dtype=torch.float32, device=mu.device)
+    term = torch.empty(1, dtype=torch.float64, device=mu.device)
+    rc = _lib.load().vibo_param_forward(C.byref(desc), H, _ptr(mu), _ptr(lv), _ptr(eps_item), _ptr(w0), _ptr(b0),
+                                        _ptr(w2), _ptr(b2), _ptr(w4), _ptr(b4), _ptr(item_feat), _ptr(table),
+                                        _ptr(hidden), _ptr(term), _stream(mu.device))
+    _lib.check(rc, "vibo_param_forward")
+    return item_feat, table, hidden, term
+
+
+def param_backward(mu, lv, eps_item, w2, w4, hidden, g_table, g_item, g_term, *, irt_model, elbo_form=ELBO_KL):
+    """vibo_param_backward -> gradients (g_mu, g_lv, g_w0, g_b0, g_w2, g_b2, g_w4, g_b4)."""
+    I, F = mu.shape
+    H = w2.shape[0]
+    D = w4.shape[0] // 2
+    desc = make_desc(0, I, D, irt_model, 0, MISSING_PRIOR, elbo_form)
+    dev = mu.device
+    outs = [torch.empty_like(mu), torch.empty_like(lv), torch.empty(H, 1, device=dev), torch.empty(H, device=dev),
+            torch.empty(H, H, device=dev), torch.empty(H, device=dev), torch.empty(2 * D, H, device=dev),
+            torch.empty(2 * D, device=dev)]
+    rc = _lib.load().vibo_param_backward(C.byref(desc), H, _ptr(mu), _ptr(lv), _ptr(eps_item), _ptr(w2), _ptr(w4),
+                                         _ptr(hidden), _ptr(g_table), _ptr(g_item), _ptr(g_term),
+                                         *[_ptr(o) for o in outs], _stream(dev))
+    _lib.check(rc, "vibo_param_backward")
+    return outs

@@ -133,6 +133,9 @@ def standard_normal_log_pdf(x):
 
 class VIBO_1PL(nn.Module):
     irt_num = 1
+    # run the parameter-side chain of the unconditional model (item reparameterisation, expert
+    # table, item prior term and their backward) in two CUDA kernels instead of PyTorch ops
+    fuse_param_chain = True
 
     def __init__(self, latent_dim, num_item, hidden_dim=64, ability_merge='mean',
                  conditional_posterior=False, generative_model='irt', response_dist='bernoulli',
@@ -282,12 +285,22 @@ class VIBO_1PL(nn.Module):
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         if eps_item is None:
             eps_item = torch.randn_like(item_feat_mu)
-        item_feat = eps_item * torch.exp(0.5 * item_feat_logvar) + item_feat_mu
-        table = self.ability_encoder.expert_table(item_feat if self.conditional_posterior else None)
+        kl_form = bool(use_kl_divergence)
+        # unconditional model on the GPU: the whole parameter-side chain is two small kernels
+        chain = (self.fuse_param_chain and item_feat_mu.is_cuda and not self.conditional_posterior
+                 and self.n_norm_flows == 0 and self.hidden_dim <= 256)
+        if chain:
+            mlp = self.ability_encoder.mlp
+            item_feat, table, item_term_raw = VF.ParamChain.apply(
+                item_feat_mu, item_feat_logvar, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias,
+                mlp[4].weight, mlp[4].bias, eps_item, self.irt_num,
+                VF.ELBO_KL if kl_form else VF.ELBO_SAMPLE)
+        else:
+            item_feat = eps_item * torch.exp(0.5 * item_feat_logvar) + item_feat_mu
+            table = self.ability_encoder.expert_table(item_feat if self.conditional_posterior else None)
         if eps_ability is None and seed is None:
             eps_ability = torch.randn(P, self.ability_dim, dtype=torch.float32, device=resp.device)
         beta = float(annealing_factor)
-        kl_form = bool(use_kl_divergence)
 
         if self.n_norm_flows > 0:
             return self._flow_elbo(resp, msk, table, item_feat, item_feat_mu, item_feat_logvar,
@@ -308,7 +321,9 @@ class VIBO_1PL(nn.Module):
         else:
             loss_k, scalars, a_mu, a_lv, ability = VF.FusedElbo.apply(
                 resp, msk, table, item_feat, eps_ability, cfg)
-        if use_kl_divergence:
+        if chain:
+            item_term = beta * item_term_raw if use_kl_divergence else item_term_raw
+        elif use_kl_divergence:
             item_term = beta * kl_divergence_standard_normal_prior(item_feat_mu, item_feat_logvar).sum()
         else:
             item_term = -(standard_normal_log_pdf(item_feat).sum()
