@@ -37,7 +37,7 @@ FusedPlan fused_plan(const vibo_desc& d) {
   const int q_mask = 16 / gcd(I, 16), q_eps = 4 / gcd(D, 4);
   const bool two_phase = d.irt_model != 3;
   const int n_teams = two_phase ? kF2Teams : kFusedTeams;
-  const int scratch = two_phase ? kF2ScratchBytes : 0;
+  auto scratch = [&](int R_, int ns_) { return two_phase ? f2_scratch_bytes(R_, ns_, D) : 0; };
   const int r_pass = (two_phase ? kF2TeamWarps : kFusedTeamWarps) * (32 / lpp);
   int r_min = r_pass;
   while (r_min % q_mask != 0 || r_min % q_eps != 0) r_min += r_pass;
@@ -49,10 +49,10 @@ FusedPlan fused_plan(const vibo_desc& d) {
   while (R > r_min && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count() * n_teams) R -= r_min;
   int ns = two_phase ? 3 : 4;  // at most 16 mbarriers per CTA
   const size_t budget = two_phase ? kSmemCap : kSmemBudget;
-  FusedSmem L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch);
+  FusedSmem L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch(R, ns));
   while (ns > 2 && L.total > budget) {
     --ns;
-    L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch);
+    L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch(R, ns));
   }
   if (L.total > budget) return pl;
   pl.two_phase = two_phase;
