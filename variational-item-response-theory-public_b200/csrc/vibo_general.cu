@@ -515,7 +515,13 @@ static cudaError_t launch_link_dm(const vibo_desc& d, const float* resp, const u
 
 cudaError_t launch_encode(const vibo_desc& d, const float* resp, const uint8_t* mask,
                           const float* table, float* mu, float* lv, float* S, cudaStream_t st) {
-  cudaError_t e = cudaSuccess;
+  cudaError_t e = stream_encode(d, resp, mask, table, mu, lv, S, nullptr, st);
+  if (e != cudaErrorNotSupported) {
+    if (e == cudaSuccess) note_launch();
+    return e;
+  }
+  (void)cudaGetLastError();
+  e = cudaSuccess;
   VIBO_SWITCH_D(d.ability_dim, e = launch_encode_d<kD>(d, resp, mask, table, mu, lv, S, st));
   return e;
 }
@@ -524,7 +530,19 @@ cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8
                               const float* table, const float* amu, const float* S,
                               const float* g_mu, const float* g_lv, float* g_table, float* part,
                               cudaStream_t st) {
-  cudaError_t e = cudaSuccess;
+  int grid = 0;
+  cudaError_t e = stream_encode_bwd(d, resp, mask, amu, S, g_mu, g_lv, part, &grid, st);
+  if (e != cudaErrorNotSupported) {
+    if (e != cudaSuccess) return e;
+    const int n = 2 * (d.conditional ? d.num_item : 1) * d.ability_dim;
+    // the stream kernel already summed over items for the unconditional table
+    encode_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(d.conditional ? d.num_item : 1, d.ability_dim,
+                                                                d.conditional, grid, part, table, g_table);
+    note_launch(2);
+    return cudaGetLastError();
+  }
+  (void)cudaGetLastError();
+  e = cudaSuccess;
   VIBO_SWITCH_D(d.ability_dim,
                 e = launch_encode_bwd_d<kD>(d, resp, mask, table, amu, S, g_mu, g_lv, g_table, part, st));
   return e;
@@ -534,7 +552,22 @@ cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* ma
                         const float* ability, const float* item_feat, double* out_ll,
                         float* g_ability, float* g_item, double* part_ll, float* part_g,
                         cudaStream_t st) {
-  cudaError_t e = cudaSuccess;
+  int grid = 0;
+  cudaError_t e = stream_link(d, resp, mask, ability, item_feat, part_ll, g_ability, part_g, g_item != nullptr,
+                              &grid, st);
+  if (e != cudaErrorNotSupported) {
+    if (e != cudaSuccess) return e;
+    sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+    note_launch(2);
+    if (g_item != nullptr) {
+      const int n = d.num_item * item_width_host(d.irt_model, d.ability_dim);
+      sum_partials_f32_kernel<<<(n + 127) / 128, 128, 0, st>>>(part_g, grid, n, 1.0f, g_item);
+      note_launch();
+    }
+    return cudaGetLastError();
+  }
+  (void)cudaGetLastError();
+  e = cudaSuccess;
   switch (d.irt_model) {
     case 1:
       VIBO_SWITCH_D(d.ability_dim, e = (launch_link_dm<kD, 1>(d, resp, mask, ability, item_feat, out_ll,

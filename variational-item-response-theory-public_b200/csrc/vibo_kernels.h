@@ -33,6 +33,18 @@ cudaError_t launch_bernoulli_ll(const vibo_desc& d, const float* resp, const uin
                                 const float* prob, double* out_ll, float* g_prob, double* part_ll,
                                 cudaStream_t st);
 
+// vibo_stream.cu: slab-stream kernels (TMA-staged row tiles).  Return
+// cudaErrorNotSupported when the configuration / pointer alignment is not
+// covered; the launchers above then fall back to the legacy kernels.
+cudaError_t stream_encode(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table,
+                          float* mu, float* lv, float* S, int* grid_out, cudaStream_t st);
+cudaError_t stream_link(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* ability,
+                        const float* item_feat, double* part_ll, float* g_ability, float* part_g, bool grad,
+                        int* grid_out, cudaStream_t st);
+cudaError_t stream_encode_bwd(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* amu,
+                              const float* S, const float* g_mu, const float* g_lv, float* part, int* grid_out,
+                              cudaStream_t st);
+
 // vibo_person.cu: per-person prior / reparameterisation math of the
 // multi-pass composition of vibo_fused_elbo.
 int person_grid(int64_t P);

@@ -1,0 +1,694 @@
+// "Slab-stream" kernels: the general (decomposed) passes of the ELBO path for
+// every variant the single-pass kernels do not cover -- conditional posterior,
+// ability_dim up to 8, 3PL, any number of items (no alignment requirement on
+// I), missing data -- at streaming speed.
+//
+//   encode_stream_kernel      product-of-experts sums   (models.py:596-629, utils.py:105-113)
+//   link_stream_kernel        link + Bernoulli log-lik  (models.py:729-766, utils.py:46-49)
+//                             + d/d ability, d/d item_feat
+//   encode_bwd_stream_kernel  per-(response value, item) sums of the expert-table gradient
+//
+// Shared skeleton.  A persistent CTA streams chunks of R rows (response f32 +
+// mask u8 + the per-person arrays the pass needs) through a ring of NS
+// shared-memory stages with 1-D TMA bulk copies completing on mbarriers; R is
+// a multiple of 16 / gcd(I, 16), which makes every block of a chunk a 16-byte
+// multiple at a 16-byte aligned address whatever I is.  Warp w owns the item
+// slab [w*32*M, (w+1)*32*M): lane l owns items w*32*M + m*32 + l (m < M) for
+// EVERY row, so item parameters, expert-table entries and per-item gradient
+// sums live in registers for the whole kernel (no atomics, deterministic) and
+// shared memory holds nothing but row data.  Per-person sums over items are
+// reduced across the 32 lanes NR rows at a time with a transpose-reduce (about
+// 4 instructions per value instead of 10 for a butterfly per value), then
+// across the slabs through shared memory in a fixed order.
+#pragma once
+
+#include "vibo_fused2_kernel.cuh"
+
+namespace vibo {
+
+constexpr int kStreamMaxStages = 8;
+constexpr int kStreamMaxParr = 4;
+
+struct StreamParams {
+  int64_t P;
+  int I;
+  int R;        // rows per stage
+  int NS;       // ring depth
+  int n_parr;   // per-person (P, D) float arrays staged with the rows
+  int D;
+  uint32_t mask_off, parr_off, stage_bytes;  // byte offsets inside a stage
+  uint32_t red_off, info_off, stage_off;      // byte offsets inside dynamic shared memory
+  const float* resp;
+  const uint8_t* mask;
+  const float* parr[kStreamMaxParr];
+};
+
+// Host-side launch plan (vibo_stream.cu).
+struct StreamPlan {
+  bool ok = false;
+  int M = 0, NW = 0, R = 0, NS = 0, grid = 0;
+  size_t smem = 0;
+  uint32_t mask_off = 0, parr_off = 0, stage_bytes = 0, red_off = 0, info_off = 0, stage_off = 0;
+};
+cudaError_t stream_link_run1(const StreamPlan& pl, const StreamParams& p, int D, const float* item_feat,
+                             double* part_ll, float* g_ability, float* part_g, bool grad, cudaStream_t st);
+cudaError_t stream_link_run2(const StreamPlan& pl, const StreamParams& p, int D, const float* item_feat,
+                             double* part_ll, float* g_ability, float* part_g, bool grad, cudaStream_t st);
+cudaError_t stream_link_run3(const StreamPlan& pl, const StreamParams& p, int D, const float* item_feat,
+                             double* part_ll, float* g_ability, float* part_g, bool grad, cudaStream_t st);
+
+// ---- staging -----------------------------------------------------------------
+// Thread 0: arm `bar` and issue the bulk copies of the full chunk c.
+__device__ __forceinline__ void stream_issue(const StreamParams& p, int64_t c, unsigned char* st, uint64_t* bar) {
+  const int64_t row0 = c * p.R;
+  const uint32_t b_resp = (uint32_t)p.R * p.I * 4, b_mask = (uint32_t)p.R * p.I, b_parr = (uint32_t)p.R * p.D * 4;
+  mbar_expect_tx(bar, b_resp + b_mask + (uint32_t)p.n_parr * b_parr);
+  bulk_g2s(st, p.resp + row0 * p.I, b_resp, bar);
+  bulk_g2s(st + p.mask_off, p.mask + row0 * p.I, b_mask, bar);
+  for (int a = 0; a < p.n_parr; ++a)
+    bulk_g2s(st + p.parr_off + (size_t)a * b_parr, p.parr[a] + row0 * p.D, b_parr, bar);
+}
+// Whole CTA: copy the ragged last chunk (rows < R; its sizes need not be
+// 16-byte multiples) by hand.
+__device__ __forceinline__ void stream_copy_ragged(const StreamParams& p, int64_t c, unsigned char* st, int rows) {
+  const int64_t row0 = c * p.R;
+  const float* gr = p.resp + row0 * p.I;
+  float* sr = reinterpret_cast<float*>(st);
+  for (int k = threadIdx.x; k < rows * p.I; k += blockDim.x) sr[k] = gr[k];
+  const uint8_t* gm = p.mask + row0 * p.I;
+  uint8_t* sm = st + p.mask_off;
+  for (int k = threadIdx.x; k < rows * p.I; k += blockDim.x) sm[k] = gm[k];
+  for (int a = 0; a < p.n_parr; ++a) {
+    const float* ga = p.parr[a] + row0 * p.D;
+    float* sa = reinterpret_cast<float*>(st + p.parr_off + (size_t)a * p.R * p.D * 4);
+    for (int k = threadIdx.x; k < rows * p.D; k += blockDim.x) sa[k] = ga[k];
+  }
+}
+
+// ---- transpose-reduce ----------------------------------------------------------
+// Each lane holds NR values (one per row).  Returns, in every lane, the sum
+// over the 32 lanes of the value of row stream_row<NR>(lane).
+template <int NR>
+__device__ __forceinline__ int stream_row(int lane) {
+  return NR == 8 ? ((lane >> 2) & 7) : ((lane >> 3) & 3);
+}
+template <int NR>
+__device__ __forceinline__ float transpose_reduce(const float (&v)[NR], int lane) {
+  static_assert(NR == 8 || NR == 4, "NR must be 4 or 8");
+  float w[NR / 2];
+  const bool b4 = (lane & 16) != 0;
+#pragma unroll
+  for (int i = 0; i < NR / 2; ++i) {
+    const float send = b4 ? v[i] : v[i + NR / 2], keep = b4 ? v[i + NR / 2] : v[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float u[NR / 4];
+  const bool b3 = (lane & 8) != 0;
+#pragma unroll
+  for (int i = 0; i < NR / 4; ++i) {
+    const float send = b3 ? w[i] : w[i + NR / 4], keep = b3 ? w[i + NR / 4] : w[i];
+    u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float t;
+  if (NR == 8) {
+    const bool b2 = (lane & 4) != 0;
+    const float send = b2 ? u[0] : u[NR == 8 ? 1 : 0], keep = b2 ? u[NR == 8 ? 1 : 0] : u[0];
+    t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  } else {
+    t = u[0] + __shfl_xor_sync(0xffffffffu, u[0], 4);
+  }
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
+}
+
+// ---- shared prologue -----------------------------------------------------------
+struct StreamCtx {
+  uint64_t* bar;
+  unsigned char* stages;
+  float* red;     // [2][R][NW][Q]
+  float* info;    // [R][..] per-row scratch
+};
+__device__ __forceinline__ StreamCtx stream_setup(const StreamParams& p, unsigned char* smem) {
+  StreamCtx c;
+  c.bar = reinterpret_cast<uint64_t*>(smem);
+  c.red = reinterpret_cast<float*>(smem + p.red_off);
+  c.info = reinterpret_cast<float*>(smem + p.info_off);
+  c.stages = smem + p.stage_off;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.NS; ++s) mbar_init(&c.bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int64_t n_full = p.P / p.R;  // chunks [0, n_full) are complete
+    for (int s = 0; s < p.NS; ++s) {
+      const int64_t ch = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (ch < n_full) stream_issue(p, ch, c.stages + (size_t)s * p.stage_bytes, &c.bar[s]);
+    }
+  }
+  __syncthreads();
+  return c;
+}
+
+// Fast logistic cell (1PL / 2PL): ll = (x-1) zc - log(1 + exp(-zc)), zc = clamp(z),
+// d ll / d z = x - sigmoid(zc), zero outside the eps32 clamp.
+__device__ __forceinline__ void cell_logistic_fast(float z, float x, float& ll, float& dz) {
+  const float zc = fminf(fmaxf(z, -kLogitClamp), kLogitClamp);
+  const float w = 1.0f + ex2_approx(zc * -kLog2e);
+  ll = fmaf(x - 1.0f, zc, -kLn2f * lg2_approx(w));
+  const float g = x - rcp_approx(w);
+  dz = (z == zc) ? g : 0.0f;
+}
+// Fast 3PL cell: p = g + (1-g) sigmoid(z) clamped to [eps32, 1-eps32] (models.py:753-766).
+__device__ __forceinline__ void cell_3pl_fast(float z, float g, bool x1, float& ll, float& dz, float& dgam) {
+  const float e = ex2_approx(fabsf(z) * -kLog2e);
+  const float r = rcp_approx(1.0f + e);
+  const float er = e * r;
+  const float s = z >= 0.0f ? r : er;    // sigmoid(z)
+  const float sn = z >= 0.0f ? er : r;   // sigmoid(-z)
+  const float p = fmaf(1.0f - g, s, g);
+  const float q = (1.0f - g) * sn;       // 1 - p with full relative precision
+  const bool inside = (p >= kEps32) && (q >= kEps32);
+  const float u = x1 ? p : q;
+  const float uc = fminf(fmaxf(u, kEps32), 1.0f - kEps32);
+  ll = kLn2f * lg2_approx(uc);
+  float dp = rcp_approx(uc);
+  dp = x1 ? dp : -dp;
+  dp = inside ? dp : 0.0f;
+  const float t = dp * sn * (1.0f - g);
+  dz = t * s;
+  dgam = t * g;
+}
+
+// ---------------------------------------------------------------------------
+// encode: S_i = sum_j tau_ij, N_i = sum_j mu_ij tau_ij  ->  mu, logvar, S
+// ---------------------------------------------------------------------------
+// Unconditional encoder (COND = false): the posterior depends on the row only
+// through the counts (n1, n_missing), so only those two sums are reduced.
+template <int D, int M, int NR, bool COND>
+__global__ void __launch_bounds__(512) encode_stream_kernel(const __grid_constant__ StreamParams p,
+                                                            int missing_policy, const float* __restrict__ table,
+                                                            float* __restrict__ out_mu, float* __restrict__ out_lv,
+                                                            float* __restrict__ out_S) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const StreamCtx cx = stream_setup(p, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+  const int I = p.I, R = p.R, NS = p.NS;
+  constexpr int Q = COND ? 2 * D : 2;
+  constexpr int DT = COND ? D : 1;   // width of the lane-owned expert registers
+
+  // lane-owned expert entries: tau0, (tau1 - tau0), mu0 tau0, (mu1 tau1 - mu0 tau0)
+  int joff[M];
+  bool valid[M];
+  float t0[M][DT], dt[M][DT], n0[M][DT], dn[M][DT];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int j = (warp * M + m) * 32 + lane;
+    valid[m] = j < I;
+    joff[m] = min(j, I - 1);
+    const int jt = joff[m], It = I;
+#pragma unroll
+    for (int d = 0; d < (COND ? D : 0); ++d) {
+      float tv[2], nv[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float mu = table[((size_t)r * It + jt) * 2 * D + d];
+        const float lam = table[((size_t)r * It + jt) * 2 * D + D + d];
+        tv[r] = 1.0f / (expf(lam) + kPoeEps);
+        nv[r] = mu * tv[r];
+      }
+      t0[m][d] = valid[m] ? tv[0] : 0.0f;
+      dt[m][d] = valid[m] ? tv[1] - tv[0] : 0.0f;
+      n0[m][d] = valid[m] ? nv[0] : 0.0f;
+      dn[m][d] = valid[m] ? nv[1] - nv[0] : 0.0f;
+    }
+  }
+  float baseS[DT], baseN[DT];   // this lane's share of sum_j tau0_j, sum_j mu0_j tau0_j
+#pragma unroll
+  for (int d = 0; d < (COND ? D : 0); ++d) {
+    baseS[d] = baseN[d] = 0.0f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      baseS[d] += t0[m][d];
+      baseN[d] += n0[m][d];
+    }
+  }
+  const float prior_tau = (missing_policy == VIBO_MISSING_PRIOR) ? 1.0f / (1.0f + kPoeEps) : 0.0f;
+
+  const int64_t n_chunks = (p.P + R - 1) / R, n_full = p.P / R;
+  int s = 0, buf = 0;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
+    const int rows = (int)((p.P - c * R < R) ? p.P - c * R : R);
+    if (c < n_full) {
+      mbar_wait(&cx.bar[s], phase);
+    } else {
+      stream_copy_ragged(p, c, st, rows);
+      __syncthreads();
+    }
+    const float* sx = reinterpret_cast<const float*>(st);
+    const uint8_t* sm = st + p.mask_off;
+    float* red = cx.red + (size_t)buf * R * NW * Q;
+    for (int r0 = 0; r0 < rows; r0 += NR) {
+      float part[Q][NR];
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const int r = r0 + rr;
+        float S[DT], N[DT], c1 = 0.0f, cm = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DT; ++d) S[d] = N[d] = 0.0f;
+        if (r < rows) {
+          float x[M];
+          bool o[M];
+          bool all_obs = true;
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            x[m] = sx[(size_t)r * I + joff[m]];
+            o[m] = sm[(size_t)r * I + joff[m]] != 0;
+            all_obs = all_obs && (o[m] || !valid[m]);
+          }
+          if (!COND) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+              c1 += (valid[m] && o[m] && x[m] > 0.5f) ? 1.0f : 0.0f;
+              cm += (valid[m] && !o[m]) ? 1.0f : 0.0f;
+            }
+          } else if (__all_sync(0xffffffffu, all_obs)) {
+#pragma unroll
+            for (int d = 0; d < DT; ++d) {
+              S[d] = baseS[d];
+              N[d] = baseN[d];
+#pragma unroll
+              for (int m = 0; m < M; ++m) {
+                S[d] = fmaf(x[m], dt[m][d], S[d]);
+                N[d] = fmaf(x[m], dn[m][d], N[d]);
+              }
+            }
+          } else {
+            float nmiss = 0.0f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+              const float wo = o[m] ? 1.0f : 0.0f, wx = o[m] ? x[m] : 0.0f;
+              nmiss += (valid[m] && !o[m]) ? 1.0f : 0.0f;
+#pragma unroll
+              for (int d = 0; d < DT; ++d) {
+                S[d] = fmaf(wo, t0[m][d], fmaf(wx, dt[m][d], S[d]));
+                N[d] = fmaf(wo, n0[m][d], fmaf(wx, dn[m][d], N[d]));
+              }
+            }
+#pragma unroll
+            for (int d = 0; d < DT; ++d) S[d] = fmaf(nmiss, prior_tau, S[d]);
+          }
+        }
+        if (COND) {
+#pragma unroll
+          for (int d = 0; d < DT; ++d) {
+            part[d][rr] = S[d];
+            part[(COND ? D : 0) + d][rr] = N[d];
+          }
+        } else {
+          part[0][rr] = c1;
+          part[1][rr] = cm;
+        }
+      }
+      const int row = r0 + stream_row<NR>(lane);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        const float t = transpose_reduce<NR>(part[k], lane);
+        if ((lane & (NR == 8 ? 3 : 7)) == 0 && row < rows) red[((size_t)row * NW + warp) * Q + k] = t;
+      }
+    }
+    __syncthreads();   // every warp is done with stage s; red[buf] is complete
+    if (threadIdx.x == 0) {
+      const int64_t cn = c + (int64_t)NS * gridDim.x;
+      if (cn < n_full) stream_issue(p, cn, st, &cx.bar[s]);
+    }
+    for (int t = threadIdx.x; t < rows * D; t += blockDim.x) {
+      const int r = t / D, d = t % D;
+      float sv = 0.0f, nv = 0.0f;
+      if (COND) {
+        for (int w = 0; w < NW; ++w) {
+          sv += red[((size_t)r * NW + w) * Q + d];
+          nv += red[((size_t)r * NW + w) * Q + D + d];
+        }
+      } else {
+        float n1 = 0.0f, nm = 0.0f;
+        for (int w = 0; w < NW; ++w) {
+          n1 += red[((size_t)r * NW + w) * Q];
+          nm += red[((size_t)r * NW + w) * Q + 1];
+        }
+        const float nz = (float)I - nm - n1;
+        const float mu0 = table[d], mu1 = table[2 * D + d];
+        const float ta0 = 1.0f / (expf(table[D + d]) + kPoeEps), ta1 = 1.0f / (expf(table[3 * D + d]) + kPoeEps);
+        sv = fmaf(nz, ta0, fmaf(n1, ta1, nm * prior_tau));
+        nv = fmaf(nz, mu0 * ta0, n1 * (mu1 * ta1));
+      }
+      const int64_t row = c * R + r;
+      out_mu[row * D + d] = nv / sv;
+      out_lv[row * D + d] = logf(1.0f / sv);
+      if (out_S) out_S[row * D + d] = sv;
+    }
+    buf ^= 1;
+    if (++s == NS) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// link + log-likelihood, d LL / d ability, d LL / d item_feat
+// ---------------------------------------------------------------------------
+// staged per-person array 0: ability (P, D).  part_gitem: [grid][I*F] with
+// d LL/d a = -sum dz theta, d LL/d b = sum dz, d LL/d gamma = sum dgam.
+template <int MODEL, int D, int M, int NR, bool GRAD>
+__global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant__ StreamParams p,
+                                                          const float* __restrict__ item_feat,
+                                                          double* __restrict__ part_ll,
+                                                          float* __restrict__ g_ability,
+                                                          float* __restrict__ part_gitem) {
+  constexpr int F = item_width(MODEL, D);
+  constexpr int DA = MODEL == 1 ? 1 : D;   // width of the discrimination registers
+  constexpr int Q = D;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const StreamCtx cx = stream_setup(p, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+  const int I = p.I, R = p.R, NS = p.NS;
+
+  int joff[M];
+  bool valid[M];
+  float a[M][DA], b[M], gs[M], acc[M][GRAD ? F : 1];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int j = (warp * M + m) * 32 + lane;
+    valid[m] = j < I;
+    joff[m] = min(j, I - 1);
+    if (MODEL == 1) {
+      b[m] = item_feat[joff[m]];
+      a[m][0] = 0.0f;
+      gs[m] = 0.0f;
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) a[m][d] = item_feat[(size_t)joff[m] * F + d];
+      b[m] = item_feat[(size_t)joff[m] * F + D];
+      gs[m] = MODEL == 3 ? 1.0f / (1.0f + expf(-item_feat[(size_t)joff[m] * F + D + 1])) : 0.0f;
+    }
+#pragma unroll
+    for (int f = 0; f < (GRAD ? F : 1); ++f) acc[m][f] = 0.0f;
+  }
+  float ll_lane = 0.0f;   // flushed into a double once per stage
+  double ll_acc = 0.0;
+
+  const int64_t n_chunks = (p.P + R - 1) / R, n_full = p.P / R;
+  int s = 0, buf = 0;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
+    const int rows = (int)((p.P - c * R < R) ? p.P - c * R : R);
+    if (c < n_full) {
+      mbar_wait(&cx.bar[s], phase);
+    } else {
+      stream_copy_ragged(p, c, st, rows);
+      __syncthreads();
+    }
+    const float* sx = reinterpret_cast<const float*>(st);
+    const uint8_t* sm = st + p.mask_off;
+    const float* sth = reinterpret_cast<const float*>(st + p.parr_off);
+    float* red = cx.red + (size_t)buf * R * NW * Q;
+    for (int r0 = 0; r0 < rows; r0 += NR) {
+      float part[GRAD ? Q : 1][NR];
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const int r = r0 + rr;
+        float gth[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) gth[d] = 0.0f;
+        if (r < rows) {
+          float th[D], tsum = 0.0f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            th[d] = sth[r * D + d];
+            tsum += th[d];
+          }
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            const float x = sx[(size_t)r * I + joff[m]];
+            const bool o = valid[m] && sm[(size_t)r * I + joff[m]] != 0;
+            float z = b[m];
+            if (MODEL == 1) {
+              z += tsum;
+            } else {
+#pragma unroll
+              for (int d = 0; d < D; ++d) z = fmaf(-th[d], a[m][d], z);
+            }
+            float ll, dz, dgam = 0.0f;
+            if (MODEL == 3) cell_3pl_fast(z, gs[m], x > 0.5f, ll, dz, dgam);
+            else cell_logistic_fast(z, x, ll, dz);
+            ll_lane += o ? ll : 0.0f;
+            if (GRAD) {
+              dz = o ? dz : 0.0f;
+              if (MODEL == 1) {
+                gth[0] += dz;
+                acc[m][0] += dz;
+              } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                  gth[d] = fmaf(-dz, a[m][d], gth[d]);
+                  acc[m][d] = fmaf(-dz, th[d], acc[m][d]);
+                }
+                acc[m][D] += dz;
+                if (MODEL == 3) acc[m][D + 1] += o ? dgam : 0.0f;
+              }
+            }
+          }
+        }
+        if (GRAD) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) part[d][rr] = MODEL == 1 ? gth[0] : gth[d];
+        }
+      }
+      if (GRAD) {
+        const int row = r0 + stream_row<NR>(lane);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+          const float t = transpose_reduce<NR>(part[k], lane);
+          if ((lane & (NR == 8 ? 3 : 7)) == 0 && row < rows) red[((size_t)row * NW + warp) * Q + k] = t;
+        }
+      }
+    }
+    ll_acc += (double)ll_lane;
+    ll_lane = 0.0f;
+    __syncthreads();   // every warp is done with stage s; red[buf] is complete
+    if (threadIdx.x == 0) {
+      const int64_t cn = c + (int64_t)NS * gridDim.x;
+      if (cn < n_full) stream_issue(p, cn, st, &cx.bar[s]);
+    }
+    if (GRAD) {
+      for (int t = threadIdx.x; t < rows * D; t += blockDim.x) {
+        const int r = t / D, d = t % D;
+        float v = 0.0f;
+        for (int w = 0; w < NW; ++w) v += red[((size_t)r * NW + w) * Q + d];
+        g_ability[(c * R + r) * D + d] = v;
+      }
+    }
+    buf ^= 1;
+    if (++s == NS) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+  if (GRAD) {
+    float* dst = part_gitem + (size_t)blockIdx.x * I * F;
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+      if (valid[m]) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) dst[(size_t)joff[m] * F + f] = acc[m][f];
+      }
+  }
+  // deterministic CTA sum of the log-likelihood
+  __syncthreads();
+  double* s_part = reinterpret_cast<double*>(cx.red);
+  const double v = warp_sum(ll_acc);
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < NW; ++w) t += s_part[w];
+    part_ll[blockIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// encode backward: A^r_j = sum_{i: o_ij, x_ij = r} GN_i,  B^r_j likewise with GS_i
+//   GN = g_mu / S,  GS = -(g_mu mu + g_lv) / S      (SURVEY Appendix A "PoE")
+// staged per-person arrays: 0 ability_mu, 1 S, 2 g_mu, 3 g_lv.
+// part: cond  -> [grid][2][I][2D] (A | B);  uncond -> [grid][2][1][2D] (summed over items)
+// ---------------------------------------------------------------------------
+template <int D, int M>
+__global__ void __launch_bounds__(512) encode_bwd_stream_kernel(const __grid_constant__ StreamParams p, int cond,
+                                                                float* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const StreamCtx cx = stream_setup(p, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+  const int I = p.I, R = p.R, NS = p.NS;
+
+  int joff[M];
+  bool valid[M];
+  float A[M][2][D], B[M][2][D];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int j = (warp * M + m) * 32 + lane;
+    valid[m] = j < I;
+    joff[m] = min(j, I - 1);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) A[m][r][d] = B[m][r][d] = 0.0f;
+  }
+  const int64_t n_chunks = (p.P + R - 1) / R, n_full = p.P / R;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
+    const int rows = (int)((p.P - c * R < R) ? p.P - c * R : R);
+    if (c < n_full) {
+      mbar_wait(&cx.bar[s], phase);
+    } else {
+      stream_copy_ragged(p, c, st, rows);
+      __syncthreads();
+    }
+    const float* sx = reinterpret_cast<const float*>(st);
+    const uint8_t* sm = st + p.mask_off;
+    const float* s_mu = reinterpret_cast<const float*>(st + p.parr_off);
+    const float* s_S = s_mu + (size_t)R * D;
+    const float* s_gm = s_S + (size_t)R * D;
+    const float* s_gl = s_gm + (size_t)R * D;
+    float* info = cx.info;   // [R][2D]: GN | GS
+    for (int t = threadIdx.x; t < rows * D; t += blockDim.x) {
+      const int r = t / D, d = t % D;
+      const float sv = s_S[t], gm = s_gm[t];
+      info[r * 2 * D + d] = gm / sv;
+      info[r * 2 * D + D + d] = -(gm * s_mu[t] + s_gl[t]) / sv;
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+      float GN[D], GS[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        GN[d] = info[r * 2 * D + d];
+        GS[d] = info[r * 2 * D + D + d];
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float x = sx[(size_t)r * I + joff[m]];
+        const bool o = valid[m] && sm[(size_t)r * I + joff[m]] != 0;
+        const float w1 = (o && x > 0.5f) ? 1.0f : 0.0f, w0 = (o && !(x > 0.5f)) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          A[m][1][d] = fmaf(w1, GN[d], A[m][1][d]);
+          B[m][1][d] = fmaf(w1, GS[d], B[m][1][d]);
+          A[m][0][d] = fmaf(w0, GN[d], A[m][0][d]);
+          B[m][0][d] = fmaf(w0, GS[d], B[m][0][d]);
+        }
+      }
+    }
+    __syncthreads();   // every warp is done with stage s and with info
+    if (threadIdx.x == 0) {
+      const int64_t cn = c + (int64_t)NS * gridDim.x;
+      if (cn < n_full) stream_issue(p, cn, st, &cx.bar[s]);
+    }
+    if (++s == NS) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+  if (cond) {
+    float* dst = part + (size_t)blockIdx.x * 2 * I * 2 * D;
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+      if (valid[m]) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            dst[((size_t)r * I + joff[m]) * 2 * D + d] = A[m][r][d];
+            dst[((size_t)r * I + joff[m]) * 2 * D + D + d] = B[m][r][d];
+          }
+      }
+  } else {
+    // unconditional table: one entry per response value -> sum over items (fixed order)
+    float* s_w = cx.red;   // [NW][4D]
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float va = 0.0f, vb = 0.0f;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          va += A[m][r][d];
+          vb += B[m][r][d];
+        }
+        va = warp_sum(va);
+        vb = warp_sum(vb);
+        if (lane == 0) {
+          s_w[warp * 4 * D + r * 2 * D + d] = va;
+          s_w[warp * 4 * D + r * 2 * D + D + d] = vb;
+        }
+      }
+    __syncthreads();
+    if ((int)threadIdx.x < 4 * D) {
+      float v = 0.0f;
+      for (int w = 0; w < NW; ++w) v += s_w[w * 4 * D + threadIdx.x];
+      part[(size_t)blockIdx.x * 4 * D + threadIdx.x] = v;
+    }
+  }
+}
+
+// Defines stream_link_run<MODEL_> in its own translation unit (compile time).
+#define VIBO_STREAM_LINK_INSTANTIATE(MODEL_, NAME_)                                                        \
+  template <int D, int M>                                                                                  \
+  static cudaError_t NAME_##_dm(const StreamPlan& pl, const StreamParams& p, const float* item_feat,       \
+                                double* part_ll, float* g_ability, float* part_g, bool grad,               \
+                                cudaStream_t st) {                                                         \
+    constexpr int NR = D <= 4 ? 8 : 4;                                                                     \
+    cudaError_t e;                                                                                         \
+    if (grad) {                                                                                            \
+      auto k = link_stream_kernel<MODEL_, D, M, NR, true>;                                                 \
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);              \
+      if (e != cudaSuccess) return e;                                                                      \
+      k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, item_feat, part_ll, g_ability, part_g);                   \
+    } else {                                                                                               \
+      auto k = link_stream_kernel<MODEL_, D, M, NR, false>;                                                \
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);              \
+      if (e != cudaSuccess) return e;                                                                      \
+      k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, item_feat, part_ll, nullptr, nullptr);                    \
+    }                                                                                                      \
+    return cudaGetLastError();                                                                             \
+  }                                                                                                        \
+  template <int D>                                                                                         \
+  static cudaError_t NAME_##_d(const StreamPlan& pl, const StreamParams& p, const float* item_feat,        \
+                               double* part_ll, float* g_ability, float* part_g, bool grad,                \
+                               cudaStream_t st) {                                                          \
+    switch (pl.M) {                                                                                        \
+      case 1: return NAME_##_dm<D, 1>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);             \
+      case 2: return NAME_##_dm<D, 2>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);             \
+      case 4: return NAME_##_dm<D, 4>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);             \
+      default: return cudaErrorInvalidValue;                                                               \
+    }                                                                                                      \
+  }                                                                                                        \
+  cudaError_t NAME_(const StreamPlan& pl, const StreamParams& p, int D, const float* item_feat,            \
+                    double* part_ll, float* g_ability, float* part_g, bool grad, cudaStream_t st) {        \
+    switch (D) {                                                                                           \
+      case 1: return NAME_##_d<1>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      case 2: return NAME_##_d<2>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      case 3: return NAME_##_d<3>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      case 4: return NAME_##_d<4>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      case 5: return NAME_##_d<5>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      case 6: return NAME_##_d<6>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      case 7: return NAME_##_d<7>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      case 8: return NAME_##_d<8>(pl, p, item_feat, part_ll, g_ability, part_g, grad, st);                 \
+      default: return cudaErrorInvalidValue;                                                               \
+    }                                                                                                      \
+  }
+
+}  // namespace vibo
