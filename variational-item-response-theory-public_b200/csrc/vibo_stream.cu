@@ -127,6 +127,107 @@ cudaError_t run_encode(const vibo_desc& d, const StreamPlan& pl, const StreamPar
   return cudaGetLastError();
 }
 
+// ---- tensor-core conditional encode --------------------------------------------
+struct MmaPlan {
+  bool ok = false;
+  int KS = 0, R = 16, NS = 0, grid = 0;
+  size_t smem = 0;
+  uint32_t mask_off = 0, parr_off = 0, stage_bytes = 0, red_off = 0, info_off = 0, stage_off = 0;
+};
+MmaPlan mma_plan(const vibo_desc& d) {
+  MmaPlan pl;
+  const int I = d.num_item, D = d.ability_dim;
+  const char* off = getenv("VIBO_DISABLE_MMA");
+  if (off != nullptr && off[0] == '1') return pl;
+  if (!d.conditional || I > 1024 || I < 16) return pl;
+  const int ksteps = (I + 15) / 16;
+  int KS = (ksteps + kMmaWarps - 1) / kMmaWarps;
+  KS = KS <= 1 ? 1 : (KS <= 2 ? 2 : (KS <= 4 ? 4 : 8));
+  const int NT = (6 * D + 7) / 8, QC = 2 * D + 1;
+  // rows per stage: multiples of 16 that keep the bulk copies 16-byte multiples
+  const int q_mask = 16 / gcd_i(I, 16);
+  int R = 16;
+  while (R % q_mask != 0) R += 16;
+  const size_t red = up((size_t)kMmaWarps * 16 * NT * 8 * 4, 128);
+  const size_t info = up(((size_t)kMmaWarps * 16 * QC + 2 * D + (size_t)I * 2 * D) * 4, 128);
+  const size_t mask_off = (size_t)R * I * 4;
+  const size_t stage = up(mask_off + (size_t)R * I, 128);
+  int NS = 4;
+  while (NS > 2 && 128 + red + info + (size_t)NS * stage > kStreamSmemCap) --NS;
+  const size_t total = 128 + red + info + (size_t)NS * stage;
+  if (total > kStreamSmemCap) return pl;
+  pl.KS = KS;
+  pl.R = R;
+  pl.NS = NS;
+  pl.smem = total;
+  pl.red_off = 128;
+  pl.info_off = (uint32_t)(128 + red);
+  pl.stage_off = (uint32_t)(128 + red + info);
+  pl.mask_off = (uint32_t)mask_off;
+  pl.parr_off = (uint32_t)stage;
+  pl.stage_bytes = (uint32_t)stage;
+  const int64_t n_chunks = (d.num_person + R - 1) / R;
+  int ctas = (int)(kStreamSmemCap / total);
+  if (ctas < 1) ctas = 1;
+  if (ctas > 4) ctas = 4;
+  int64_t g = (int64_t)sm_count() * ctas;
+  if (g > n_chunks) g = n_chunks;
+  if (g < 1) g = 1;
+  pl.grid = (int)g;
+  pl.ok = true;
+  return pl;
+}
+
+// ---- tensor-core encode backward (conditional table) ----------------------------
+struct BwdMmaPlan {
+  bool ok = false;
+  int MT = 0, grid = 0;
+  StreamPlan sp;
+};
+BwdMmaPlan bwd_mma_plan(const vibo_desc& d) {
+  BwdMmaPlan pl;
+  const int I = d.num_item, D = d.ability_dim;
+  const char* off = getenv("VIBO_DISABLE_MMA");
+  if (off != nullptr && off[0] == '1') return pl;
+  if (!d.conditional || I > 1024 || I < 16) return pl;
+  const int NT = (4 * D + 7) / 8, NC = NT * 8, NW = 16;
+  const int MT = I <= 256 ? 1 : (I <= 512 ? 2 : 4);
+  if (MT * NT * 8 > 96) return pl;   // accumulator registers
+  const int q_mask = 16 / gcd_i(I, 16), q_parr = 4 / gcd_i(D, 4);
+  int rq = 8;
+  while (rq % q_mask != 0 || rq % q_parr != 0) rq += 8;
+  int R = rq;
+  const size_t row_bytes = (size_t)I * 5 + 4 * (size_t)D * 4;
+  while ((size_t)(R + rq) * row_bytes <= 40 * 1024 && R + rq <= 64) R += rq;
+  while (R > rq && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count()) R -= rq;
+  const size_t red = up((size_t)R * NC * 4 + 256, 128), info = 128;
+  const size_t mask_off = (size_t)R * I * 4;
+  const size_t parr_off = up(mask_off + (size_t)R * I, 16);
+  const size_t stage = up(parr_off + 4 * (size_t)R * D * 4, 128);
+  const size_t tile = (size_t)NW * 16 * MT * NC * 4;   // epilogue staging reuses the stages
+  int NS = 5;
+  while (NS > 2 && 128 + red + info + (size_t)NS * stage > kStreamSmemCap) --NS;
+  size_t total = 128 + red + info + (size_t)NS * stage;
+  if (total > kStreamSmemCap) return pl;
+  if ((size_t)NS * stage < tile) total = 128 + red + info + tile;
+  if (total > kStreamSmemCap) return pl;
+  pl.sp.M = 0; pl.sp.NW = NW; pl.sp.R = R; pl.sp.NS = NS; pl.sp.smem = total;
+  pl.sp.red_off = 128;
+  pl.sp.info_off = (uint32_t)(128 + red);
+  pl.sp.stage_off = (uint32_t)(128 + red + info);
+  pl.sp.mask_off = (uint32_t)mask_off;
+  pl.sp.parr_off = (uint32_t)parr_off;
+  pl.sp.stage_bytes = (uint32_t)stage;
+  const int64_t n_chunks = (d.num_person + R - 1) / R;
+  int64_t g = sm_count();
+  if (g > n_chunks) g = n_chunks;
+  if (g < 1) g = 1;
+  pl.grid = pl.sp.grid = (int)g;
+  pl.MT = MT;
+  pl.ok = true;
+  return pl;
+}
+
 template <int D, int M>
 cudaError_t run_encode_bwd(const vibo_desc& d, const StreamPlan& pl, const StreamParams& p, float* part,
                            cudaStream_t st) {
@@ -166,6 +267,18 @@ cudaError_t run_encode_bwd(const vibo_desc& d, const StreamPlan& pl, const Strea
 cudaError_t stream_encode(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table,
                           float* mu, float* lv, float* S, int* grid_out, cudaStream_t st) {
   if (!aligned16(resp) || !aligned16(mask)) return cudaErrorNotSupported;
+  const MmaPlan mp = mma_plan(d);
+  if (mp.ok) {
+    StreamPlan sp;
+    sp.R = mp.R; sp.NS = mp.NS; sp.mask_off = mp.mask_off; sp.parr_off = mp.parr_off;
+    sp.stage_bytes = mp.stage_bytes; sp.red_off = mp.red_off; sp.info_off = mp.info_off; sp.stage_off = mp.stage_off;
+    const StreamParams p = make_params(d, sp, resp, mask, 0, nullptr);
+    cudaError_t e = cudaSuccess;
+    e = stream_encode_mma_run(d.ability_dim, mp.KS, (d.num_item & 1) == 0, mp.grid, mp.smem, p, d.missing_policy,
+                              table, mu, lv, S, st);
+    if (grid_out) *grid_out = mp.grid;
+    return e;
+  }
   const StreamPlan pl = stream_plan(d, 0, 0);
   if (!pl.ok) return cudaErrorNotSupported;
   const StreamParams p = make_params(d, pl, resp, mask, 0, nullptr);
@@ -201,9 +314,17 @@ cudaError_t stream_encode_bwd(const vibo_desc& d, const float* resp, const uint8
   if (!aligned16(resp) || !aligned16(mask) || !aligned16(amu) || !aligned16(S) || !aligned16(g_mu) ||
       !aligned16(g_lv))
     return cudaErrorNotSupported;
+  const float* parr[4] = {amu, S, g_mu, g_lv};
+  const BwdMmaPlan mp = bwd_mma_plan(d);
+  if (mp.ok) {
+    const StreamParams p = make_params(d, mp.sp, resp, mask, 4, parr);
+    cudaError_t e = cudaSuccess;
+    e = stream_encode_bwd_mma_run(d.ability_dim, mp.MT, mp.grid, mp.sp.smem, p, part, st);
+    if (grid_out) *grid_out = mp.grid;
+    return e;
+  }
   const StreamPlan pl = stream_plan(d, 2, 4);
   if (!pl.ok) return cudaErrorNotSupported;
-  const float* parr[4] = {amu, S, g_mu, g_lv};
   const StreamParams p = make_params(d, pl, resp, mask, 4, parr);
   cudaError_t e = cudaSuccess;
   VIBO_STREAM_SWITCH_D(d.ability_dim, VIBO_STREAM_SWITCH_M(pl.M, e = (run_encode_bwd<kD, kM>(d, pl, p, part, st))));

@@ -57,6 +57,12 @@ cudaError_t stream_link_run2(const StreamPlan& pl, const StreamParams& p, int D,
 cudaError_t stream_link_run3(const StreamPlan& pl, const StreamParams& p, int D, const float* item_feat,
                              double* part_ll, float* g_ability, float* part_g, bool grad, cudaStream_t st);
 
+cudaError_t stream_encode_mma_run(int D, int KS, bool even, int grid, size_t smem, const StreamParams& p,
+                                  int missing_policy, const float* table, float* mu, float* lv, float* S,
+                                  cudaStream_t st);
+cudaError_t stream_encode_bwd_mma_run(int D, int MT, int grid, size_t smem, const StreamParams& p, float* part,
+                                      cudaStream_t st);
+
 // ---- staging -----------------------------------------------------------------
 // Thread 0: arm `bar` and issue the bulk copies of the full chunk c.
 __device__ __forceinline__ void stream_issue(const StreamParams& p, int64_t c, unsigned char* st, uint64_t* bar) {
@@ -262,8 +268,8 @@ __global__ void __launch_bounds__(512) encode_stream_kernel(const __grid_constan
           bool all_obs = true;
 #pragma unroll
           for (int m = 0; m < M; ++m) {
-            x[m] = sx[(size_t)r * I + joff[m]];
-            o[m] = sm[(size_t)r * I + joff[m]] != 0;
+            x[m] = sx[r * I + joff[m]];
+            o[m] = sm[r * I + joff[m]] != 0;
             all_obs = all_obs && (o[m] || !valid[m]);
           }
           if (!COND) {
@@ -431,8 +437,8 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
           }
 #pragma unroll
           for (int m = 0; m < M; ++m) {
-            const float x = sx[(size_t)r * I + joff[m]];
-            const bool o = valid[m] && sm[(size_t)r * I + joff[m]] != 0;
+            const float x = sx[r * I + joff[m]];
+            const bool o = valid[m] && sm[r * I + joff[m]] != 0;
             float z = b[m];
             if (MODEL == 1) {
               z += tsum;
@@ -580,8 +586,8 @@ __global__ void __launch_bounds__(512) encode_bwd_stream_kernel(const __grid_con
       }
 #pragma unroll
       for (int m = 0; m < M; ++m) {
-        const float x = sx[(size_t)r * I + joff[m]];
-        const bool o = valid[m] && sm[(size_t)r * I + joff[m]] != 0;
+        const float x = sx[r * I + joff[m]];
+        const bool o = valid[m] && sm[r * I + joff[m]] != 0;
         const float w1 = (o && x > 0.5f) ? 1.0f : 0.0f, w0 = (o && !(x > 0.5f)) ? 1.0f : 0.0f;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -611,8 +617,8 @@ __global__ void __launch_bounds__(512) encode_bwd_stream_kernel(const __grid_con
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            dst[((size_t)r * I + joff[m]) * 2 * D + d] = A[m][r][d];
-            dst[((size_t)r * I + joff[m]) * 2 * D + D + d] = B[m][r][d];
+            dst[(r * I + joff[m]) * 2 * D + d] = A[m][r][d];
+            dst[(r * I + joff[m]) * 2 * D + D + d] = B[m][r][d];
           }
       }
   } else {
@@ -641,6 +647,498 @@ __global__ void __launch_bounds__(512) encode_bwd_stream_kernel(const __grid_con
       for (int w = 0; w < NW; ++w) v += s_w[w * 4 * D + threadIdx.x];
       part[(size_t)blockIdx.x * 4 * D + threadIdx.x] = v;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Conditional encode on the tensor cores.
+//
+// With a conditional posterior the product-of-experts sums are a matrix product
+// with the 0/1 response matrix:  S_i[d] = sum_j tau0_jd + sum_j (o x)_ij (tau1 - tau0)_jd
+// (N likewise), i.e. (rows x items) . (items x 2D).  The response indicator is
+// exact in bf16; the table differences are split into three bf16 terms
+// (hi + mid + lo = 24 significant bits, summed back in fp32), so the product
+// carries fp32 accuracy:  columns = [S hi|mid|lo, N hi|mid|lo] = 6 D.
+// mma.sync m16n8k16 (bf16 in, fp32 accumulate): this shape -- K = items up to
+// 1024, N = 6 D <= 48, HBM-bound -- has no use for a tcgen05/TMEM pipeline.
+//
+// Work split: the 8 warps of a CTA split the items (K) of a 16-row tile:
+// warp w owns k-steps [w*KS, (w+1)*KS) of 16 items each and keeps their B
+// fragments in registers for the whole kernel; the partial 16 x 6D tiles are
+// summed across warps through shared memory in a fixed order.  Missing cells
+// (sparse) are corrected on the CUDA cores: S -= tau0_j, N -= mu0_j tau0_j,
+// plus the prior expert's precision under VIBO_MISSING_PRIOR.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float bf16_round(float v) {
+  uint32_t u = __float_as_uint(v);
+  u += 0x7fffu + ((u >> 16) & 1u);   // round to nearest even on the upper 16 bits (finite inputs)
+  return __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {   // both already bf16-representable
+  return (__float_as_uint(lo) >> 16) | (__float_as_uint(hi) & 0xffff0000u);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// expert entries of item j, dimension d: tau0, tau1 - tau0, mu0 tau0, mu1 tau1 - mu0 tau0
+__device__ __forceinline__ void expert_entry(const float* __restrict__ table, int I, int D, int j, int d, float& t0,
+                                             float& dt, float& n0, float& dn) {
+  const float mu0 = table[((size_t)j) * 2 * D + d], lam0 = table[((size_t)j) * 2 * D + D + d];
+  const float mu1 = table[((size_t)I + j) * 2 * D + d], lam1 = table[((size_t)I + j) * 2 * D + D + d];
+  t0 = 1.0f / (expf(lam0) + kPoeEps);
+  const float t1 = 1.0f / (expf(lam1) + kPoeEps);
+  dt = t1 - t0;
+  n0 = mu0 * t0;
+  dn = mu1 * t1 - n0;
+}
+
+// smem (after the barrier block): red [NW][16][NT*8] | corr [NW][16][2D+1] | base [2D] |
+// tab [I][2D] (tau0 | mu0 tau0, for the missing-cell correction) | stages
+constexpr int kMmaWarps = 8;
+template <int D, int KS, bool EVEN>
+__global__ void __launch_bounds__(kMmaWarps * 32) encode_mma_kernel(const __grid_constant__ StreamParams p, int missing_policy,
+                                                         const float* __restrict__ table,
+                                                         float* __restrict__ out_mu, float* __restrict__ out_lv,
+                                                         float* __restrict__ out_S) {
+  constexpr int NT = (6 * D + 7) / 8, NC = NT * 8, QC = 2 * D + 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const StreamCtx cx = stream_setup(p, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int I = p.I, R = p.R, NS = p.NS;
+  float* red = cx.red;                       // [NW][16][NC]
+  float* corr = cx.info;                     // [NW][16][QC]
+  float* base = corr + (size_t)NW * 16 * QC;   // [2D]
+  float* tab = base + 2 * D;                   // [I][2D]
+  int* sflag = reinterpret_cast<int*>(smem + 64);   // behind the (<= 8) mbarriers
+
+  // ---- B fragments of this warp's k-steps (registers, whole kernel) ----------
+  // b0: rows k = 2t, 2t+1 of the k-step, column n = g of the n-tile; b1: rows 2t+8, 2t+9.
+  uint32_t bf[KS][NT][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int j0 = 16 * (warp * KS + ks) + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = 8 * nt + g;
+      const int kind = col / (3 * D), sp = (col % (3 * D)) / D, d = col % D;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + (e & 1) + (e >> 1) * 8;
+        float val = 0.0f;
+        if (j < I && col < 6 * D) {
+          float t0, dt, n0, dn;
+          expert_entry(table, I, D, j, d, t0, dt, n0, dn);
+          const float full = kind == 0 ? dt : dn;
+          const float hi = bf16_round(full), mid = bf16_round(full - hi), lo = bf16_round(full - hi - mid);
+          val = sp == 0 ? hi : (sp == 1 ? mid : lo);
+        }
+        v[e] = val;
+      }
+      bf[ks][nt][0] = pack_bf16x2(v[0], v[1]);
+      bf[ks][nt][1] = pack_bf16x2(v[2], v[3]);
+    }
+  }
+  for (int k = threadIdx.x; k < I * D; k += blockDim.x) {
+    const int j = k / D, d = k % D;
+    float t0, dt, n0, dn;
+    expert_entry(table, I, D, j, d, t0, dt, n0, dn);
+    tab[j * 2 * D + d] = t0;
+    tab[j * 2 * D + D + d] = n0;
+  }
+  __syncthreads();
+  // base sums over all items, fixed order (thread k < 2D)
+  if ((int)threadIdx.x < 2 * D) {
+    float acc = 0.0f;
+    for (int j = 0; j < I; ++j) acc += tab[j * 2 * D + threadIdx.x];
+    base[threadIdx.x] = acc;
+  }
+  const float prior_tau = (missing_policy == VIBO_MISSING_PRIOR) ? 1.0f / (1.0f + kPoeEps) : 0.0f;
+  __syncthreads();
+
+  const int64_t n_chunks = (p.P + R - 1) / R, n_full = p.P / R;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
+    const int rows = (int)((p.P - c * R < R) ? p.P - c * R : R);
+    if (threadIdx.x == 0) *sflag = 0;
+    if (c < n_full) {
+      mbar_wait(&cx.bar[s], phase);
+    } else {
+      stream_copy_ragged(p, c, st, rows);
+    }
+    __syncthreads();
+    const float* sx = reinterpret_cast<const float*>(st);
+    const uint8_t* sm = st + p.mask_off;
+    // any zero byte in the stage's mask block?  (16 bytes per load)
+    {
+      bool miss = false;
+      const uint4* m4 = reinterpret_cast<const uint4*>(sm);
+      const int n16 = (rows * I) >> 4;
+      for (int k = threadIdx.x; k < n16; k += blockDim.x) {
+        const uint4 w = m4[k];
+        const uint32_t z = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                           ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+        miss = miss || (z & 0x80808080u) != 0;
+      }
+      for (int k = (n16 << 4) + threadIdx.x; k < rows * I; k += blockDim.x) miss = miss || sm[k] == 0;
+      if (miss) *sflag = 1;
+    }
+    __syncthreads();
+    const bool has_missing = *sflag != 0;
+    for (int r0 = 0; r0 < rows; r0 += 16) {
+      float C[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) C[nt][0] = C[nt][1] = C[nt][2] = C[nt][3] = 0.0f;
+      float cs[2][D], cn[2][D], cnt[2] = {0.0f, 0.0f};   // missing-cell corrections of rows g, g+8
+#pragma unroll
+      for (int d = 0; d < D; ++d) cs[0][d] = cs[1][d] = cn[0][d] = cn[1][d] = 0.0f;
+      const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int jbase = 16 * (warp * KS + ks);
+        if (jbase < I) {   // warp-uniform
+          uint32_t a[4];
+          bool miss[8];
+          bool any_miss = false;
+          if (EVEN && r0 + 16 <= rows && jbase + 16 <= I) {
+            // interior tile: unguarded 64-bit loads; a 0/1 float's upper half IS its bf16
+            const float* xa = sx + ra * I + jbase + 2 * t;
+            const float2 x0 = *reinterpret_cast<const float2*>(xa);
+            const float2 x1 = *reinterpret_cast<const float2*>(xa + 8 * I);
+            const float2 x2 = *reinterpret_cast<const float2*>(xa + 8);
+            const float2 x3 = *reinterpret_cast<const float2*>(xa + 8 * I + 8);
+            a[0] = __byte_perm(__float_as_uint(x0.x), __float_as_uint(x0.y), 0x7632);
+            a[1] = __byte_perm(__float_as_uint(x1.x), __float_as_uint(x1.y), 0x7632);
+            a[2] = __byte_perm(__float_as_uint(x2.x), __float_as_uint(x2.y), 0x7632);
+            a[3] = __byte_perm(__float_as_uint(x3.x), __float_as_uint(x3.y), 0x7632);
+            uint32_t mm[4] = {0x0101u, 0x0101u, 0x0101u, 0x0101u};
+            if (has_missing) {
+              const uint8_t* ma = sm + ra * I + jbase + 2 * t;
+              mm[0] = *reinterpret_cast<const uint16_t*>(ma);
+              mm[1] = *reinterpret_cast<const uint16_t*>(ma + 8 * I);
+              mm[2] = *reinterpret_cast<const uint16_t*>(ma + 8);
+              mm[3] = *reinterpret_cast<const uint16_t*>(ma + 8 * I + 8);
+            }
+            // all eight mask bytes non-zero?
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (!has_missing) {
+                miss[((k & 1) ? 2 : 0) + ((k & 2) ? 4 : 0)] = miss[((k & 1) ? 2 : 0) + ((k & 2) ? 4 : 0) + 1] = false;
+                continue;
+              }
+              const bool lo_miss = (mm[k] & 0xffu) == 0, hi_miss = (mm[k] & 0xff00u) == 0;
+              // e index: bit0 column within the pair, bit1 row half, bit2 column half
+              const int e0 = ((k & 1) ? 2 : 0) + ((k & 2) ? 4 : 0);
+              miss[e0] = lo_miss;
+              miss[e0 + 1] = hi_miss;
+              any_miss = any_miss || lo_miss || hi_miss;
+              if (lo_miss) a[k] &= 0xffff0000u;   // a missing cell holds -1: drop it from the product
+              if (hi_miss) a[k] &= 0x0000ffffu;
+            }
+          } else {
+            float w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int r = (e & 2) ? rb : ra;
+              const int j = jbase + 2 * t + (e & 1) + ((e & 4) ? 8 : 0);
+              const bool in = r < rows && j < I;
+              float x = 0.0f;
+              bool o = true;
+              if (in) {
+                x = sx[r * I + j];
+                o = sm[r * I + j] != 0;
+              }
+              w[e] = (in && o) ? x : 0.0f;
+              miss[e] = in && !o;
+              any_miss = any_miss || miss[e];
+            }
+            a[0] = pack_bf16x2(w[0], w[1]);   // row g,   cols 2t, 2t+1
+            a[1] = pack_bf16x2(w[2], w[3]);   // row g+8, cols 2t, 2t+1
+            a[2] = pack_bf16x2(w[4], w[5]);   // row g,   cols 2t+8, 2t+9
+            a[3] = pack_bf16x2(w[6], w[7]);   // row g+8, cols 2t+8, 2t+9
+          }
+          if (any_miss) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (miss[e]) {
+                const int j = jbase + 2 * t + (e & 1) + ((e & 4) ? 8 : 0);
+                const int h = (e & 2) ? 1 : 0;
+                cnt[h] += 1.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                  cs[h][d] += tab[j * 2 * D + d];
+                  cn[h][d] += tab[j * 2 * D + D + d];
+                }
+              }
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(C[nt], a, bf[ks][nt]);
+        }
+      }
+      // partial tile -> shared memory;  C: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+      float* rw = red + (size_t)warp * 16 * NC;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        *reinterpret_cast<float2*>(&rw[g * NC + 8 * nt + 2 * t]) = make_float2(C[nt][0], C[nt][1]);
+        *reinterpret_cast<float2*>(&rw[(g + 8) * NC + 8 * nt + 2 * t]) = make_float2(C[nt][2], C[nt][3]);
+      }
+      float* cw = corr + (size_t)warp * 16 * QC;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!has_missing) break;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          float v = cs[h][d], u = cn[h][d];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          u += __shfl_xor_sync(0xffffffffu, u, 1);
+          u += __shfl_xor_sync(0xffffffffu, u, 2);
+          if (t == 0) {
+            cw[(g + 8 * h) * QC + d] = v;
+            cw[(g + 8 * h) * QC + D + d] = u;
+          }
+        }
+        float k = cnt[h];
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        if (t == 0) cw[(g + 8 * h) * QC + 2 * D] = k;
+      }
+      __syncthreads();
+      const int tile_rows = min(16, rows - r0);
+      for (int q = threadIdx.x; q < tile_rows * D; q += blockDim.x) {
+        const int r = q / D, d = q % D;
+        float sv = 0.0f, nv = 0.0f, cS = 0.0f, cN = 0.0f, cm = 0.0f;
+        for (int w2 = 0; w2 < NW; ++w2) {
+          const float* rr = red + ((size_t)w2 * 16 + r) * NC;
+          sv += (rr[d] + rr[D + d]) + rr[2 * D + d];
+          nv += (rr[3 * D + d] + rr[4 * D + d]) + rr[5 * D + d];
+          if (has_missing) {
+            const float* cc = corr + ((size_t)w2 * 16 + r) * QC;
+            cS += cc[d];
+            cN += cc[D + d];
+            cm += cc[2 * D];
+          }
+        }
+        sv = (base[d] - cS) + sv + cm * prior_tau;
+        nv = (base[D + d] - cN) + nv;
+        const int64_t row = c * R + r0 + r;
+        out_mu[row * D + d] = nv / sv;
+        out_lv[row * D + d] = logf(1.0f / sv);
+        if (out_S) out_S[row * D + d] = sv;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const int64_t cn2 = c + (int64_t)NS * gridDim.x;
+      if (cn2 < n_full) stream_issue(p, cn2, st, &cx.bar[s]);
+    }
+    if (++s == NS) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Encode backward on the tensor cores (conditional table).
+//
+//   A^r_j[d] = sum_i [o_ij, x_ij = r] GN_i[d],   B^r_j[d] likewise with GS_i
+// is (items x rows) . (rows x 2D) with a 0/1 left operand.  TF32 mma.sync
+// m16n8k8 holds ONE element per fragment register, so the transposed operand
+// W^T[item][row] is read straight from the row-major stage (no transposition
+// pass); the right operand [GN | GS] is split into two TF32 terms (22
+// significant bits) -> columns = [hi(2D) | lo(2D)].  Two accumulator sets: the
+// x = 1 indicator and the observed indicator (A^0 = A^obs - A^1); for a stage
+// without missing cells the observed product does not depend on the item and
+// collapses to a column sum of G kept by 4D threads.
+// Warp w owns items [w*16*MT, (w+1)*16*MT) and keeps their accumulators in
+// registers for the whole kernel (deterministic).
+// smem: red = G tile [R][NC] | info: flags, column sums | stages
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int D, int MT>
+__global__ void __launch_bounds__(512) encode_bwd_mma_kernel(const __grid_constant__ StreamParams p,
+                                                             float* __restrict__ part) {
+  constexpr int NT = (4 * D + 7) / 8, NC = NT * 8;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const StreamCtx cx = stream_setup(p, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int I = p.I, R = p.R, NS = p.NS;
+  float* Gs = cx.red;                                   // [R][NC] tf32 bit patterns
+  int* flag = reinterpret_cast<int*>(cx.info);          // [0]: stage has a missing cell
+  float T1[MT][NT][4], To[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) T1[mt][nt][k] = To[mt][nt][k] = 0.0f;
+  float gfull = 0.0f;   // thread c < NC: sum over fully observed stages of G[.][c]
+  const int j0 = warp * 16 * MT;
+
+  const int64_t n_chunks = (p.P + R - 1) / R, n_full = p.P / R;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
+    const int rows = (int)((p.P - c * R < R) ? p.P - c * R : R);
+    if (threadIdx.x == 0) flag[0] = 0;
+    if (c < n_full) {
+      mbar_wait(&cx.bar[s], phase);
+    } else {
+      stream_copy_ragged(p, c, st, rows);
+    }
+    __syncthreads();
+    const float* sx = reinterpret_cast<const float*>(st);
+    const uint8_t* sm = st + p.mask_off;
+    const float* s_mu = reinterpret_cast<const float*>(st + p.parr_off);
+    const float* s_S = s_mu + (size_t)R * D;
+    const float* s_gm = s_S + (size_t)R * D;
+    const float* s_gl = s_gm + (size_t)R * D;
+    // ---- stage prep: G tile (two TF32 terms), missing-cell flag --------------
+    for (int q = threadIdx.x; q < R * NC; q += blockDim.x) {
+      const int r = q / NC, col = q % NC;
+      float v = 0.0f;
+      if (r < rows && col < 4 * D) {
+        const int sp = col / (2 * D), k = col % (2 * D), d = k % D;
+        const float sv = s_S[r * D + d], gm = s_gm[r * D + d];
+        const float full = k < D ? gm / sv : -(gm * s_mu[r * D + d] + s_gl[r * D + d]) / sv;
+        const float hi = tf32_round(full);
+        v = sp == 0 ? hi : tf32_round(full - hi);
+      }
+      Gs[q] = v;
+    }
+    {
+      // any zero byte in the stage's mask block?  (16 bytes per load; mask bytes are 0 / 1)
+      bool miss = false;
+      const uint4* m4 = reinterpret_cast<const uint4*>(sm);
+      const int n16 = (rows * I) >> 4;
+      for (int k = threadIdx.x; k < n16; k += blockDim.x) {
+        const uint4 w = m4[k];
+        const uint32_t z = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                           ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+        miss = miss || (z & 0x80808080u) != 0;
+      }
+      for (int k = (n16 << 4) + threadIdx.x; k < rows * I; k += blockDim.x) miss = miss || sm[k] == 0;
+      if (miss) flag[0] = 1;
+    }
+    __syncthreads();
+    const bool has_missing = flag[0] != 0;
+    if (!has_missing && (int)threadIdx.x < NC) {
+      float acc = 0.0f;
+      for (int r = 0; r < rows; ++r) acc += Gs[r * NC + threadIdx.x];
+      gfull += acc;
+    }
+    if (j0 < I) {
+      for (int k0 = 0; k0 < rows; k0 += 8) {
+        uint32_t bfr[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          bfr[nt][0] = __float_as_uint(Gs[(k0 + t) * NC + 8 * nt + g]);       // rows >= `rows` hold zeros
+          bfr[nt][1] = __float_as_uint(Gs[(k0 + t + 4) * NC + 8 * nt + g]);
+        }
+        if (!has_missing && k0 + 8 <= rows && j0 + 16 * MT <= I) {
+          // interior, fully observed: a 0/1 response IS its TF32 operand
+          const float* xb = sx + (k0 + t) * I + j0 + g;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            uint32_t a1[4];
+            a1[0] = __float_as_uint(xb[16 * mt]);
+            a1[1] = __float_as_uint(xb[16 * mt + 8]);
+            a1[2] = __float_as_uint(xb[4 * I + 16 * mt]);
+            a1[3] = __float_as_uint(xb[4 * I + 16 * mt + 8]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32_1688(T1[mt][nt], a1, bfr[nt]);
+          }
+          continue;
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          // a0: (item g, row t)  a1: (item g+8, row t)  a2: (item g, row t+4)  a3: (item g+8, row t+4)
+          uint32_t a1[4], ao[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j0 + 16 * mt + g + ((e & 1) ? 8 : 0);
+            const int r = k0 + t + ((e & 2) ? 4 : 0);
+            const bool in = j < I && r < rows;
+            const int jj = in ? j : 0, rr = in ? r : 0;
+            const float x = sx[rr * I + jj];
+            const bool o = in && (has_missing ? sm[rr * I + jj] != 0 : true);
+            a1[e] = (o && x > 0.5f) ? 0x3f800000u : 0u;
+            ao[e] = o ? 0x3f800000u : 0u;
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma_tf32_1688(T1[mt][nt], a1, bfr[nt]);
+          if (has_missing) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32_1688(To[mt][nt], ao, bfr[nt]);
+          }
+        }
+      }
+    }
+    __syncthreads();   // every warp is done with stage s, Gs and flag
+    if (threadIdx.x == 0) {
+      const int64_t cn = c + (int64_t)NS * gridDim.x;
+      if (cn < n_full) stream_issue(p, cn, st, &cx.bar[s]);
+    }
+    if (++s == NS) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+  // ---- epilogue: per-item sums -> global partials -----------------------------
+  // stage memory is free: tile [I_pad][NC], one accumulator set at a time; the two
+  // TF32 terms are added and A^0 = A^obs - A^1.
+  __syncthreads();
+  float* tile = reinterpret_cast<float*>(cx.stages);
+  float* gf = Gs;   // [NC]
+  if ((int)threadIdx.x < NC) gf[threadIdx.x] = gfull;
+  float* dst = part + (size_t)blockIdx.x * 2 * I * 2 * D;
+#pragma unroll
+  for (int set = 0; set < 2; ++set) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        // c0 (item g, col 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+        const int ja = j0 + 16 * mt + g, jb = ja + 8, col = 8 * nt + 2 * t;
+        const float (&T)[4] = set == 0 ? T1[mt][nt] : To[mt][nt];
+        tile[(size_t)ja * NC + col] = T[0];
+        tile[(size_t)ja * NC + col + 1] = T[1];
+        tile[(size_t)jb * NC + col] = T[2];
+        tile[(size_t)jb * NC + col + 1] = T[3];
+      }
+    __syncthreads();
+    for (int q = threadIdx.x; q < I * 2 * D; q += blockDim.x) {
+      const int j = q / (2 * D), k = q % (2 * D);
+      const float v = tile[(size_t)j * NC + k] + tile[(size_t)j * NC + 2 * D + k];
+      if (set == 0) {
+        dst[((size_t)1 * I + j) * 2 * D + k] = v;
+      } else {
+        const float vo = v + (gf[k] + gf[2 * D + k]);
+        dst[((size_t)0 * I + j) * 2 * D + k] = vo - dst[((size_t)1 * I + j) * 2 * D + k];
+      }
+    }
+    __syncthreads();
   }
 }
 
