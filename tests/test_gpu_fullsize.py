@@ -85,3 +85,53 @@ def test_full_size_linearity_in_grad_scale_and_beta():
     g = [K.fused_elbo(resp, mask, table, item, eps, irt_model=2, conditional=False, beta=b)["g_table"].double()
          for b in (0.0, 0.5, 1.0)]
     assert _rel(g[2] - g[1], g[1] - g[0]) < 1e-4
+
+
+@pytest.mark.parametrize("missing", [0.0, 0.05])
+def test_conditional_paths_agree_at_scale(monkeypatch, missing):
+    """C3's shape (3PL, ability-dim 5, conditional posterior, 1000 items) on enough rows that
+    every CTA walks its stage ring several times, with a ragged last chunk: the tensor-core
+    path, the slab-stream path and the legacy kernels must agree."""
+    import vibo_b200
+    K = vibo_b200.kernels
+    P, I, D = 60_013, 1000, 5
+    resp, mask = _rows(P, I, missing, seed=11)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    table = 0.4 * torch.randn(2, I, 2 * D, generator=g, device="cuda")
+    item = 0.5 * torch.randn(I, D + 2, generator=g, device="cuda")
+    eps = torch.randn(P, D, generator=g, device="cuda")
+    kw = dict(irt_model=3, conditional=True, beta=0.7, want_person_outputs=True)
+    monkeypatch.setenv("VIBO_DISABLE_FUSED", "1")
+    a = K.fused_elbo(resp, mask, table, item, eps, **kw)                 # mma encode / encode-backward
+    monkeypatch.setenv("VIBO_DISABLE_MMA", "1")
+    b = K.fused_elbo(resp, mask, table, item, eps, **kw)                 # slab-stream
+    monkeypatch.setenv("VIBO_DISABLE_STREAM", "1")
+    c = K.fused_elbo(resp, mask, table, item, eps, **kw)                 # legacy
+    for other, name in ((b, "slab"), (c, "legacy")):
+        assert _rel(a["scalars"], other["scalars"]) < 1e-6, name
+        for k in ("ability_mu", "ability_logvar", "ability"):
+            assert _rel(a[k], other[k]) < 1e-5, (name, k)
+        assert _rel(a["g_item"], other["g_item"]) < 1e-4, (name, _rel(a["g_item"], other["g_item"]))
+        assert _rel(a["g_table"], other["g_table"]) < 1e-4, (name, _rel(a["g_table"], other["g_table"]))
+    again = K.fused_elbo(resp, mask, table, item, eps, **kw)
+    for k in ("scalars", "g_item", "g_table"):
+        assert torch.equal(c[k], again[k]), f"{k} not bit-reproducible"
+
+
+def test_unaligned_items_paths_agree_at_scale(monkeypatch):
+    """C5's shape (95 items: rows are not 16-byte multiples, 10 % missing) at full size."""
+    import vibo_b200
+    K = vibo_b200.kernels
+    P, I = 428_478, 95
+    resp, mask = _rows(P, I, 0.1, seed=21)
+    table, item = _params(I, 1, 2, seed=22)
+    eps = torch.randn(P, 1, device="cuda")
+    kw = dict(irt_model=2, conditional=False, beta=1.0, want_person_outputs=True)
+    a = K.fused_elbo(resp, mask, table, item, eps, **kw)                 # slab-stream
+    monkeypatch.setenv("VIBO_DISABLE_STREAM", "1")
+    b = K.fused_elbo(resp, mask, table, item, eps, **kw)                 # legacy
+    assert _rel(a["scalars"], b["scalars"]) < 1e-6
+    for k in ("ability_mu", "ability_logvar", "ability"):
+        assert _rel(a[k], b[k]) < 1e-5, k
+    assert _rel(a["g_item"], b["g_item"]) < 1e-5
+    assert _rel(a["g_table"], b["g_table"]) < 1e-5

@@ -79,13 +79,25 @@ GRID = [
 ]
 
 
-@pytest.mark.parametrize("composed", [False, True], ids=["fused", "composed"])
+# which implementation serves the call:
+#   fused    - single-pass kernel where it applies, else the composition below
+#   composed - three passes: tensor-core (mma.sync) encode / encode-backward for a conditional
+#              posterior, slab-stream kernels otherwise
+#   slab     - three passes, slab-stream kernels only (VIBO_DISABLE_MMA=1)
+#   legacy   - three passes, the original row-slab kernels (unaligned-pointer fallback)
+PATHS = {"fused": {}, "composed": {"VIBO_DISABLE_FUSED": "1"},
+         "slab": {"VIBO_DISABLE_FUSED": "1", "VIBO_DISABLE_MMA": "1"},
+         "legacy": {"VIBO_DISABLE_FUSED": "1", "VIBO_DISABLE_MMA": "1", "VIBO_DISABLE_STREAM": "1"}}
+
+
+@pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("P,I,D,irt,cond,missing,policy,form", GRID)
-def test_fused_elbo_vs_oracle(vb, monkeypatch, P, I, D, irt, cond, missing, policy, form, composed):
-    """vibo_fused_elbo: single-pass kernel where it applies, and (composed) the
-    three-pass composition of the general kernels on the same inputs."""
-    if composed:
-        monkeypatch.setenv("VIBO_DISABLE_FUSED", "1")
+def test_fused_elbo_vs_oracle(vb, monkeypatch, P, I, D, irt, cond, missing, policy, form, path):
+    """vibo_fused_elbo against the fp64 oracle, through every implementation path."""
+    for k, v in PATHS[path].items():
+        monkeypatch.setenv(k, v)
+    if path == "legacy" and I > 1024 and D > 4:
+        pytest.skip("legacy kernels: I <= 1024 for D > 4")
     resp, mask, table, item, eps = _synth(P, I, D, irt, cond, missing, seed=P * 7 + I)
     beta = 0.7
     got = _run_fused(vb, resp, mask, table, item, eps, irt_model=irt, conditional=cond,

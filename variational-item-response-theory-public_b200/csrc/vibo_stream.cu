@@ -27,6 +27,7 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   if (off != nullptr && off[0] == '1') return pl;
   // items per lane: the register budget of the lane-owned state bounds M
   int M = I <= 512 ? 1 : (I <= 1024 ? 2 : 4);
+  if (kind == 1 && M == 1) M = 2;   // the link kernel works on f32x2 pairs of items
   if (I > 2048) return pl;
   const int F = d.irt_model == 1 ? 1 : (d.irt_model == 2 ? D + 1 : D + 2);
   const int regs = kind == 0 ? (d.conditional ? 4 * D : 0) : (kind == 1 ? 2 * F + 2 : 4 * D);
@@ -62,7 +63,9 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
     return 128 + red + info + (size_t)NS_ * stage;
   };
   // grow R while a stage stays <= 24 KB and R <= 64, then fit NS
-  while ((size_t)(R + rq) * row_bytes <= 24 * 1024 && R + rq <= 64 && total(R + rq, 2, nullptr) <= budget) R += rq;
+  // long rows (one CTA per SM): 16-row stages halve the number of CTA-wide barriers per row
+  const size_t stage_cap = (ctas == 1 ? 84 : 24) * 1024;
+  while ((size_t)(R + rq) * row_bytes <= stage_cap && R + rq <= 64 && total(R + rq, 2, nullptr) <= budget) R += rq;
   // small problems: keep enough chunks to occupy the machine
   while (R > rq && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count() * ctas) R -= rq;
   while (NS > 2 && total(R, NS, nullptr) > budget) --NS;
@@ -198,7 +201,7 @@ BwdMmaPlan bwd_mma_plan(const vibo_desc& d) {
   while (rq % q_mask != 0 || rq % q_parr != 0) rq += 8;
   int R = rq;
   const size_t row_bytes = (size_t)I * 5 + 4 * (size_t)D * 4;
-  while ((size_t)(R + rq) * row_bytes <= 40 * 1024 && R + rq <= 64) R += rq;
+  while ((size_t)(R + rq) * row_bytes <= 84 * 1024 && R + rq <= 64) R += rq;
   while (R > rq && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count()) R -= rq;
   const size_t red = up((size_t)R * NC * 4 + 256, 128), info = 128;
   const size_t mask_off = (size_t)R * I * 4;

@@ -22,6 +22,8 @@
 // across the slabs through shared memory in a fixed order.
 #pragma once
 
+#include <type_traits>
+
 #include "vibo_fused2_kernel.cuh"
 
 namespace vibo {
@@ -366,6 +368,39 @@ __global__ void __launch_bounds__(512) encode_stream_kernel(const __grid_constan
 // ---------------------------------------------------------------------------
 // staged per-person array 0: ability (P, D).  part_gitem: [grid][I*F] with
 // d LL/d a = -sum dz theta, d LL/d b = sum dz, d LL/d gamma = sum dgam.
+//
+// One cell of the link.  3PL: p = g + (1-g) sigmoid(z), clamped to [eps32, 1-eps32]
+// (models.py:753-766; the clamp is torch.distributions' clamp_probs).  With
+// E = exp(-max(z,-80)), r = 1/(1+E): sigmoid(z) = r, sigmoid(-z) = E r (full relative
+// precision on both sides), u = x ? p : 1-p, ll = log clamp(u), and
+//   t0 = d ll/d u * sigmoid(-z) (signed, zero outside the clamp):
+//   d ll/d z = t0 sigmoid(z) (1-g),   d ll/d gamma = t0 g (1-g)   (g (1-g) is applied per item at the end).
+// wv: 1 for a lane-owned item that exists, 0 for padding (j >= I): d ll/d z is scaled by
+// it so that padding lanes drop out of the per-person sums without selects.
+template <int MODEL>
+__device__ __forceinline__ void link_cell(float z, float x, float g, float omg, float wv, float& ll, float& dz,
+                                          float& t0) {
+  if (MODEL == 3) {
+    const float zc = fmaxf(z, -80.0f);
+    const float e = ex2_approx(zc * -kLog2e);
+    const float r = rcp_approx(1.0f + e);
+    const float sn = e * r;
+    const float pp = fmaf(omg, r, g), q = omg * sn;
+    const bool x1 = x > 0.5f;
+    const float u = x1 ? pp : q;
+    const float uc = fminf(fmaxf(u, kEps32), 1.0f - kEps32);
+    ll = kLn2f * lg2_approx(uc);
+    float dp = rcp_approx(uc) * fmaf(x, 2.0f, -1.0f);   // +1/p for x = 1, -1/(1-p) for x = 0
+    dp = (uc == u) ? dp : 0.0f;
+    t0 = dp * sn;
+    dz = t0 * r * (omg * wv);   // omg * wv is loop-invariant per item
+  } else {
+    cell_logistic_fast(z, x, ll, dz);
+    dz *= wv;
+    t0 = 0.0f;
+  }
+}
+
 template <int MODEL, int D, int M, int NR, bool GRAD>
 __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant__ StreamParams p,
                                                           const float* __restrict__ item_feat,
@@ -375,37 +410,73 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
   constexpr int F = item_width(MODEL, D);
   constexpr int DA = MODEL == 1 ? 1 : D;   // width of the discrimination registers
   constexpr int Q = D;
+  constexpr int MP = (M + 1) / 2;          // the lane's items are handled as f32x2 pairs
   extern __shared__ __align__(128) unsigned char smem[];
   const StreamCtx cx = stream_setup(p, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
   const int I = p.I, R = p.R, NS = p.NS;
+  int* sflag = reinterpret_cast<int*>(smem + 64);   // [2]: "stage has a missing cell", by chunk parity
 
-  int joff[M];
-  bool valid[M];
-  float a[M][DA], b[M], gs[M], acc[M][GRAD ? F : 1];
+  int joff[2 * MP];
+  bool valid[2 * MP];
+  f2_t a2[MP][DA], b2[MP], acc2[MP][GRAD ? F : 1];   // pairs over the lane's items (2k, 2k+1)
+  float gs[2 * MP], omg[2 * MP], wv[2 * MP];
 #pragma unroll
-  for (int m = 0; m < M; ++m) {
-    const int j = (warp * M + m) * 32 + lane;
-    valid[m] = j < I;
-    joff[m] = min(j, I - 1);
-    if (MODEL == 1) {
-      b[m] = item_feat[joff[m]];
-      a[m][0] = 0.0f;
-      gs[m] = 0.0f;
-    } else {
+  for (int k = 0; k < MP; ++k) {
+    float av[2][DA], bv[2];
 #pragma unroll
-      for (int d = 0; d < D; ++d) a[m][d] = item_feat[(size_t)joff[m] * F + d];
-      b[m] = item_feat[(size_t)joff[m] * F + D];
-      gs[m] = MODEL == 3 ? 1.0f / (1.0f + expf(-item_feat[(size_t)joff[m] * F + D + 1])) : 0.0f;
+    for (int h = 0; h < 2; ++h) {
+      const int m = 2 * k + h;
+      const int j = (warp * M + m) * 32 + lane;
+      valid[m] = m < M && j < I;
+      joff[m] = min(j, I - 1);
+      if (MODEL == 1) {
+        bv[h] = item_feat[joff[m]];
+        av[h][0] = 0.0f;
+        gs[m] = 0.0f;
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) av[h][d] = item_feat[(size_t)joff[m] * F + d];
+        bv[h] = item_feat[(size_t)joff[m] * F + D];
+        gs[m] = MODEL == 3 ? 1.0f / (1.0f + expf(-item_feat[(size_t)joff[m] * F + D + 1])) : 0.0f;
+      }
+      omg[m] = 1.0f - gs[m];
+      wv[m] = valid[m] ? 1.0f : 0.0f;
     }
+    b2[k] = pack2(bv[0], bv[1]);
 #pragma unroll
-    for (int f = 0; f < (GRAD ? F : 1); ++f) acc[m][f] = 0.0f;
+    for (int d = 0; d < DA; ++d) a2[k][d] = pack2(av[0][d], av[1][d]);
+#pragma unroll
+    for (int f = 0; f < (GRAD ? F : 1); ++f) acc2[k][f] = pack2(0.0f, 0.0f);
   }
   float ll_lane = 0.0f;   // flushed into a double once per stage
   double ll_acc = 0.0;
 
   const int64_t n_chunks = (p.P + R - 1) / R, n_full = p.P / R;
-  int s = 0, buf = 0;
+  // 16 mask bytes per thread per load: does the stage hold a missing cell?
+  auto scan_missing = [&](const unsigned char* st_, int rows_) {
+    bool miss = false;
+    const uint4* m4 = reinterpret_cast<const uint4*>(st_ + p.mask_off);
+    const int n16 = (rows_ * I) >> 4;
+    for (int k = threadIdx.x; k < n16; k += blockDim.x) {
+      const uint4 w = m4[k];
+      const uint32_t zz = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                          ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+      miss = miss || (zz & 0x80808080u) != 0;
+    }
+    return miss;
+  };
+  if (threadIdx.x < 2) sflag[threadIdx.x] = 0;
+  __syncthreads();
+  if ((int64_t)blockIdx.x < n_full) {
+    mbar_wait(&cx.bar[0], 0);
+    if (scan_missing(cx.stages, R)) sflag[0] = 1;
+  } else if (threadIdx.x == 0) {
+    sflag[0] = 1;   // ragged first chunk: take the masked path
+  }
+  __syncthreads();
+
+  int s = 0, buf = 0, par = 0;
   uint32_t phase = 0;
   for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
@@ -416,53 +487,73 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
       stream_copy_ragged(p, c, st, rows);
       __syncthreads();
     }
+    const bool has_missing = sflag[par] != 0;
     const float* sx = reinterpret_cast<const float*>(st);
     const uint8_t* sm = st + p.mask_off;
     const float* sth = reinterpret_cast<const float*>(st + p.parr_off);
     float* red = cx.red + (size_t)buf * R * NW * Q;
-    for (int r0 = 0; r0 < rows; r0 += NR) {
+    // One tile of NR rows.  MASKED: consult the mask / item validity / row count;
+    // otherwise every cell of the tile is a valid observed cell (no selects).
+    auto tile = [&](int r0, auto omask_tag, auto ragged_tag) {
+      constexpr bool OMASK = decltype(omask_tag)::value;     // consult the mask bytes
+      constexpr bool RAGGED = decltype(ragged_tag)::value;   // the tile may run past `rows`
       float part[GRAD ? Q : 1][NR];
+      const float* xr = sx + r0 * I;
+      const uint8_t* mr = sm + r0 * I;
+      const float* tr = sth + r0 * D;
 #pragma unroll
-      for (int rr = 0; rr < NR; ++rr) {
-        const int r = r0 + rr;
+      for (int rr = 0; rr < NR; ++rr, xr += I, mr += I, tr += D) {
         float gth[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) gth[d] = 0.0f;
-        if (r < rows) {
+        if (!RAGGED || r0 + rr < rows) {
           float th[D], tsum = 0.0f;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            th[d] = sth[r * D + d];
+            th[d] = tr[d];
             tsum += th[d];
           }
 #pragma unroll
-          for (int m = 0; m < M; ++m) {
-            const float x = sx[r * I + joff[m]];
-            const bool o = valid[m] && sm[r * I + joff[m]] != 0;
-            float z = b[m];
+          for (int k = 0; k < MP; ++k) {
+            float x[2], ll[2], dz[2], t0[2];
+            f2_t z2 = b2[k];
             if (MODEL == 1) {
-              z += tsum;
+              z2 = add2(z2, pack2(tsum, tsum));
             } else {
 #pragma unroll
-              for (int d = 0; d < D; ++d) z = fmaf(-th[d], a[m][d], z);
+              for (int d = 0; d < D; ++d) z2 = fma2(pack2(-th[d], -th[d]), a2[k][d], z2);
             }
-            float ll, dz, dgam = 0.0f;
-            if (MODEL == 3) cell_3pl_fast(z, gs[m], x > 0.5f, ll, dz, dgam);
-            else cell_logistic_fast(z, x, ll, dz);
-            ll_lane += o ? ll : 0.0f;
+            float z[2];
+            unpack2(z2, z[0], z[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int m = 2 * k + h;
+              x[h] = xr[joff[m]];
+              link_cell<MODEL>(z[h], x[h], gs[m], omg[m], wv[m], ll[h], dz[h], t0[h]);
+              if (OMASK) {
+                const bool o = mr[joff[m]] != 0;
+                ll[h] = o ? ll[h] : 0.0f;
+                dz[h] = o ? dz[h] : 0.0f;
+                t0[h] = o ? t0[h] : 0.0f;
+              }
+              ll_lane = fmaf(wv[m], ll[h], ll_lane);
+            }
             if (GRAD) {
-              dz = o ? dz : 0.0f;
+              const f2_t dz2 = pack2(dz[0], dz[1]);
               if (MODEL == 1) {
-                gth[0] += dz;
-                acc[m][0] += dz;
+                gth[0] += dz[0] + dz[1];
+                acc2[k][0] = add2(acc2[k][0], dz2);
               } else {
+                const f2_t ndz2 = pack2(-dz[0], -dz[1]);
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                  gth[d] = fmaf(-dz, a[m][d], gth[d]);
-                  acc[m][d] = fmaf(-dz, th[d], acc[m][d]);
+                  float lo, hi;
+                  unpack2(a2[k][d], lo, hi);
+                  gth[d] = fmaf(-dz[0], lo, fmaf(-dz[1], hi, gth[d]));
+                  acc2[k][d] = fma2(ndz2, pack2(th[d], th[d]), acc2[k][d]);
                 }
-                acc[m][D] += dz;
-                if (MODEL == 3) acc[m][D + 1] += o ? dgam : 0.0f;
+                acc2[k][D] = add2(acc2[k][D], dz2);
+                if (MODEL == 3) acc2[k][D + 1] = add2(acc2[k][D + 1], pack2(t0[0], t0[1]));
               }
             }
           }
@@ -477,13 +568,40 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
           const float t = transpose_reduce<NR>(part[k], lane);
-          if ((lane & (NR == 8 ? 3 : 7)) == 0 && row < rows) red[((size_t)row * NW + warp) * Q + k] = t;
+          if ((lane & (NR == 8 ? 3 : 7)) == 0 && (!RAGGED || row < rows))
+            red[((size_t)row * NW + warp) * Q + k] = t;
         }
       }
+    };
+    int r0 = 0;
+    if (has_missing) {
+      for (; r0 + NR <= rows; r0 += NR) tile(r0, std::true_type{}, std::false_type{});
+      if (r0 < rows) tile(r0, std::true_type{}, std::true_type{});
+    } else {
+      for (; r0 + NR <= rows; r0 += NR) tile(r0, std::false_type{}, std::false_type{});
+      if (r0 < rows) tile(r0, std::false_type{}, std::true_type{});
     }
     ll_acc += (double)ll_lane;
     ll_lane = 0.0f;
-    __syncthreads();   // every warp is done with stage s; red[buf] is complete
+    // look ahead: does the next chunk of this CTA hold a missing cell?  (its copy was
+    // issued NS chunks ago, so this wait is normally free)
+    {
+      const int64_t cnext = c + gridDim.x;
+      if (threadIdx.x == 0) sflag[par ^ 1] = (cnext < n_chunks && cnext >= n_full) ? 1 : 0;
+      __syncwarp();
+      if (cnext < n_full) {
+        const int sn2 = s + 1 == NS ? 0 : s + 1;
+        mbar_wait(&cx.bar[sn2], sn2 == 0 ? phase ^ 1u : phase);
+      }
+    }
+    __syncthreads();   // every warp is done with stage s; red[buf] is complete; sflag[par^1] is reset
+    {
+      const int64_t cnext = c + gridDim.x;
+      if (cnext < n_full) {
+        const int sn2 = s + 1 == NS ? 0 : s + 1;
+        if (scan_missing(cx.stages + (size_t)sn2 * p.stage_bytes, R)) sflag[par ^ 1] = 1;
+      }
+    }
     if (threadIdx.x == 0) {
       const int64_t cn = c + (int64_t)NS * gridDim.x;
       if (cn < n_full) stream_issue(p, cn, st, &cx.bar[s]);
@@ -496,7 +614,9 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
         g_ability[(c * R + r) * D + d] = v;
       }
     }
+    __syncthreads();   // sflag[par^1] is final
     buf ^= 1;
+    par ^= 1;
     if (++s == NS) {
       s = 0;
       phase ^= 1u;
@@ -505,11 +625,20 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
   if (GRAD) {
     float* dst = part_gitem + (size_t)blockIdx.x * I * F;
 #pragma unroll
-    for (int m = 0; m < M; ++m)
-      if (valid[m]) {
+    for (int k = 0; k < MP; ++k) {
 #pragma unroll
-        for (int f = 0; f < F; ++f) dst[(size_t)joff[m] * F + f] = acc[m][f];
+      for (int f = 0; f < F; ++f) {
+        float v[2];
+        unpack2(acc2[k][f], v[0], v[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = 2 * k + h;
+          // 3PL guess logit: d ll/d gamma = g (1 - g) sum t0
+          const float sc = (MODEL == 3 && f == D + 1) ? gs[m] * omg[m] : 1.0f;
+          if (valid[m]) dst[(size_t)joff[m] * F + f] = v[h] * sc;
+        }
       }
+    }
   }
   // deterministic CTA sum of the log-likelihood
   __syncthreads();
