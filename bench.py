@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--mode", default="eval", choices=["train", "eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extra-workloads", default="c3,c5",
+                    help="other BASELINE.json configs timed after the headline at N=1 (comma list, '' = none)")
     ap.add_argument("--cuda-graph", type=int, default=1, help="capture the step in a CUDA graph (1/0)")
     args = ap.parse_args()
 
@@ -373,6 +375,48 @@ def main():
                        "with the kernel) -> loss read back"}
         del resp_h, mask_h
 
+    # The other single-GPU BASELINE.json configurations (parity-test cases, not the
+    # headline): same step definitions, fewer steps, reported under "other_configs".
+    # They run the multi-pass composition (tensor-core / slab-stream kernels): each
+    # pass streams the 5 B/cell matrix once -> 2 passes per eval, 3 per train step.
+    other_configs = {}
+    if world == 1 and args.extra_workloads:
+        del resp, mask, model, trainer
+        torch.cuda.empty_cache()
+        for wname in [w for w in args.extra_workloads.split(",") if w and w != args.workload]:
+            try:
+                irt2, P2, I2, D2, cond2, miss2, flows2 = WORKLOADS[wname]
+                r2, m2 = synth_rows(P2, I2, D2, irt2, miss2, dev, seed=42)
+                torch.manual_seed(42)
+                cls2 = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[irt2]
+                model2 = cls2(D2, I2, hidden_dim=64, ability_merge="product", conditional_posterior=cond2,
+                              n_norm_flows=flows2).to(dev)
+                tr2 = vdist.ShardedElboTrainer(model2, lr=5e-3, world_size=1, rank=0, person_offset=0,
+                                               use_kl_divergence=(flows2 == 0), cuda_graph=bool(args.cuda_graph))
+                rec = {"workload": describe(wname), "single_pass_kernel": bool(tr2.uses_fused)}
+                for mode2, passes in (("eval", 2), ("train", 3)):
+                    fn = tr2.eval_step if mode2 == "eval" else tr2.train_step
+                    for i in range(3):
+                        fn(r2, m2, step_index=i)
+                    torch.cuda.synchronize()
+                    k2 = max(3, min(args.steps, 10))
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    for i in range(k2):
+                        o2 = fn(r2, m2, step_index=3 + i)
+                    a1.record()
+                    torch.cuda.synchronize()
+                    ms2 = a0.elapsed_time(a1) / k2
+                    npass = 1 if tr2.uses_fused else passes
+                    gbs = P2 * I2 * BYTES_PER_CELL * npass / (ms2 * 1e-3) / 1e9
+                    rec[mode2] = {"ms_per_step": ms2, "cells_per_s": P2 * I2 / (ms2 * 1e-3), "loss": float(o2.item()),
+                                  "passes_over_rows": npass, "hbm_gbs_algorithmic": gbs, "frac_of_peak": gbs / peak}
+                other_configs[wname] = rec
+                del r2, m2, model2, tr2
+                torch.cuda.empty_cache()
+            except Exception as ex:  # an extra must never take the headline line down
+                other_configs[wname] = {"error": repr(ex)[:200]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_reference_cpu(args.workload, 3, 1, args.mode)
@@ -397,6 +441,7 @@ def main():
                 "evals_per_sec": main_res["evals_per_sec"], "loss": main_res["loss"],
                 "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": main_res["clocks"],
+                "other_configs": other_configs or None,
                 ("train_step" if other_mode == "train" else "eval_step"): other_res}
         print(json.dumps(line))
     if world > 1:

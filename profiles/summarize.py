@@ -3,6 +3,7 @@ under profiles/ (run in the build container, no GPU needed):
 
     python profiles/summarize.py launches gpurun_out/r01_launches_c4.csv profiles/r01_launches_c4_summary.md
     python profiles/summarize.py kernel   gpurun_out/r01_fused2_eval_c4.ncu-rep c4 eval
+    python profiles/summarize.py multi    gpurun_out/r01_c3_kernels.ncu-rep c3 "C3 multi-pass kernels"
 
 `kernel` appends/updates profiles/fused_kernel_ncu.json (read by bench.py for
 roofline.traffic) and writes profiles/<report>_summary.md.
@@ -97,8 +98,48 @@ def kernel(rep, workload, mode):
     print("wrote", md, "and", js)
 
 
+def multi(rep, workload, title):
+    """Every kernel of a multi-kernel `ncu --set full` report -> one markdown summary
+    and profiles/multipass_kernels_ncu.json (keyed by workload / kernel)."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    js = os.path.join(HERE, "multipass_kernels_ncu.json")
+    allrec = json.load(open(js)) if os.path.exists(js) else {}
+    md = os.path.join(HERE, os.path.basename(rep).replace(".ncu-rep", "_summary.md"))
+    with open(md, "w") as f:
+        f.write(f"# ncu --set full summary: {title}\n\nworkload {workload}, report `{os.path.basename(rep)}` "
+                f"(`--clock-control none`, launches after warm-up)\n")
+        seen = set()
+        for d in rows[2:]:
+            name = d[hdr.index("Kernel Name")]
+            short = name.split("(")[0]
+            if short in seen:
+                continue
+            seen.add(short)
+            rec = {"kernel": name, "report": os.path.basename(rep)}
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    rec[k] = {"value": float(d[i].replace(",", "")), "unit": units[i]}
+            stalls = {h.split("issue_stalled_")[1].split("_per_")[0]: float(d[i])
+                      for i, h in enumerate(hdr) if "issue_stalled" in h and h.endswith("ratio")}
+            rec["stall_ratio_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1]))
+            allrec.setdefault(workload, {})[short] = rec
+            f.write(f"\n## `{short}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in KEYS:
+                if k in rec:
+                    f.write(f"| {k} | {rec[k]['value']:.6g} | {rec[k]['unit']} |\n")
+            top = list(rec["stall_ratio_per_issue"].items())[:6]
+            f.write("\nstalls per issued instruction: " + ", ".join(f"{k} {v:.2f}" for k, v in top) + "\n")
+    json.dump(allrec, open(js, "w"), indent=1)
+    print("wrote", md, "and", js)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "multi":
+        multi(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         kernel(sys.argv[2], sys.argv[3], sys.argv[4])

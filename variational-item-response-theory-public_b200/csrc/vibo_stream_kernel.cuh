@@ -825,6 +825,38 @@ __device__ __forceinline__ void expert_entry(const float* __restrict__ table, in
   dn = mu1 * t1 - n0;
 }
 
+// A fragment of an edge tile: element e (bit0 column within the pair, bit1 row half g / g+8,
+// bit2 column half +8) is the response where the cell exists and is observed, else 0.
+struct MmaAFrag {
+  uint32_t a0, a1, a2, a3, miss;
+};
+static __device__ __noinline__ MmaAFrag mma_a_guarded(const float* sx, const uint8_t* sm, int I, int rows, int ra, int rb,
+                                               int j0) {
+  float w[8];
+  uint32_t miss = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int r = (e & 2) ? rb : ra;
+    const int j = j0 + (e & 1) + ((e & 4) ? 8 : 0);
+    const bool in = r < rows && j < I;
+    float x = 0.0f;
+    bool o = true;
+    if (in) {
+      x = sx[r * I + j];
+      o = sm[r * I + j] != 0;
+    }
+    w[e] = (in && o) ? x : 0.0f;
+    if (in && !o) miss |= 1u << e;
+  }
+  MmaAFrag f;
+  f.a0 = pack_bf16x2(bf16_round(w[0]), bf16_round(w[1]));   // row g,   cols 2t, 2t+1
+  f.a1 = pack_bf16x2(bf16_round(w[2]), bf16_round(w[3]));   // row g+8, cols 2t, 2t+1
+  f.a2 = pack_bf16x2(bf16_round(w[4]), bf16_round(w[5]));   // row g,   cols 2t+8, 2t+9
+  f.a3 = pack_bf16x2(bf16_round(w[6]), bf16_round(w[7]));   // row g+8, cols 2t+8, 2t+9
+  f.miss = miss;
+  return f;
+}
+
 // smem (after the barrier block): red [NW][16][NT*8] | corr [NW][16][2D+1] | base [2D] |
 // tab [I][2D] (tau0 | mu0 tau0, for the missing-cell correction) | stages
 constexpr int kMmaWarps = 8;
@@ -972,26 +1004,12 @@ __global__ void __launch_bounds__(kMmaWarps * 32) encode_mma_kernel(const __grid
               if (hi_miss) a[k] &= 0x0000ffffu;
             }
           } else {
-            float w[8];
+            // edge tile (ragged rows / items, odd I): guarded scalar loads, kept out of line
+            const MmaAFrag fr = mma_a_guarded(sx, sm, I, rows, ra, rb, jbase + 2 * t);
+            a[0] = fr.a0; a[1] = fr.a1; a[2] = fr.a2; a[3] = fr.a3;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int r = (e & 2) ? rb : ra;
-              const int j = jbase + 2 * t + (e & 1) + ((e & 4) ? 8 : 0);
-              const bool in = r < rows && j < I;
-              float x = 0.0f;
-              bool o = true;
-              if (in) {
-                x = sx[r * I + j];
-                o = sm[r * I + j] != 0;
-              }
-              w[e] = (in && o) ? x : 0.0f;
-              miss[e] = in && !o;
-              any_miss = any_miss || miss[e];
-            }
-            a[0] = pack_bf16x2(w[0], w[1]);   // row g,   cols 2t, 2t+1
-            a[1] = pack_bf16x2(w[2], w[3]);   // row g+8, cols 2t, 2t+1
-            a[2] = pack_bf16x2(w[4], w[5]);   // row g,   cols 2t+8, 2t+9
-            a[3] = pack_bf16x2(w[6], w[7]);   // row g+8, cols 2t+8, 2t+9
+            for (int e = 0; e < 8; ++e) miss[e] = (fr.miss >> e) & 1u;
+            any_miss = fr.miss != 0;
           }
           if (any_miss) {
 #pragma unroll
