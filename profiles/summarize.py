@@ -101,12 +101,15 @@ def kernel(rep, workload, mode):
 def multi(rep, workload, title):
     """Every kernel of a multi-kernel `ncu --set full` report -> one markdown summary
     and profiles/multipass_kernels_ncu.json (keyed by workload / kernel)."""
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):   # raw page exported on the GPU box (`ncu -i rep --page raw --csv`)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     js = os.path.join(HERE, "multipass_kernels_ncu.json")
     allrec = json.load(open(js)) if os.path.exists(js) else {}
-    md = os.path.join(HERE, os.path.basename(rep).replace(".ncu-rep", "_summary.md"))
+    md = os.path.join(HERE, os.path.basename(rep).replace(".ncu-rep", "_summary.md").replace("_raw.csv", "_summary.md"))
     with open(md, "w") as f:
         f.write(f"# ncu --set full summary: {title}\n\nworkload {workload}, report `{os.path.basename(rep)}` "
                 f"(`--clock-control none`, launches after warm-up)\n")
