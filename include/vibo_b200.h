@@ -196,6 +196,34 @@ int vibo_param_backward(const vibo_desc* desc, int hidden_dim, const float* mu_l
                         float* g_w4, float* g_b4, void* stream);
 
 /*
+ * Planar normalizing flows on the abilities (--n-norm-flows K), per person and
+ * fused with the reparameterised draw and the person-side terms of the flow
+ * form of the ELBO [flows.py:21-41, :58-66; models.py:342-348, :406-424]:
+ *
+ *   theta_0 = ability_mu + eps * exp(ability_logvar / 2)             [models.py:506-510]
+ *   theta_k = theta_{k-1} + uhat_k tanh(w_k . theta_{k-1} + b_k)     [flows.py:21-41]
+ *   ldj_k   = log(|1 + (1 - tanh^2) (w_k . uhat_k)| + 1e-8)
+ *   out_term (double[1]) = sum_i [ log N(theta_K; 0, 1) - log N(theta_0; mu, exp logvar)
+ *                                  + sum_k ldj_k ]                   [models.py:412-424]
+ *
+ * uhat (K, D) is the invertibility-corrected u of flows.py:26-29, formed by the
+ * caller from (u, w) (parameter-only arithmetic); w (K, D), b (K).  ability_0
+ * (P, D) may be NULL.  K <= 8.  The backward returns d loss / d (ability_mu,
+ * ability_logvar) (P, D) and d loss / d (uhat, w, b) given g_ability_k =
+ * d loss / d theta_K (P, D) and g_term = d loss / d out_term (device float[1]).
+ */
+int vibo_flow_person_forward(const vibo_desc* desc, int n_flows, const float* ability_mu,
+                             const float* ability_logvar, const float* eps, const float* uhat,
+                             const float* w, const float* b, float* ability_0, float* ability_k,
+                             double* out_term, void* workspace, size_t workspace_bytes, void* stream);
+int vibo_flow_person_backward(const vibo_desc* desc, int n_flows, const float* ability_mu,
+                              const float* ability_logvar, const float* eps, const float* uhat,
+                              const float* w, const float* b, const float* g_ability_k,
+                              const float* g_term, float* g_ability_mu, float* g_ability_logvar,
+                              float* g_uhat, float* g_w, float* g_b, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/*
  * Measurement hooks (used by bench.py; no effect on results).
  *   vibo_launch_count      kernels this library has launched in this process.
  *   vibo_profile_begin     start bracketing every launch of the fused kernel

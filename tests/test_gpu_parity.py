@@ -76,6 +76,15 @@ GRID = [
     (64, 2048, 1, 2, False, 0.0, 0, 0),
     (3, 5, 1, 2, False, 0.0, 0, 0),
     (1, 1, 1, 1, False, 0.0, 0, 0),
+    # tensor-core / slab-stream edge cases: odd item counts, exact tile multiples, every D, ragged rows
+    (100, 999, 5, 3, True, 0.1, 0, 0),
+    (50, 1024, 8, 2, True, 0.0, 0, 0),
+    (70, 512, 6, 3, True, 0.3, 0, 0),
+    (33, 16, 1, 2, True, 0.5, 0, 0),
+    (40, 17, 2, 1, True, 0.0, 0, 0),
+    (45, 640, 7, 3, True, 0.05, 1, 1),
+    (64, 2000, 3, 2, True, 0.1, 0, 0),
+    (64, 1500, 2, 3, False, 0.2, 0, 0),
 ]
 
 
@@ -296,3 +305,44 @@ def test_bad_arguments_raise(vb):
     with pytest.raises(vb._lib.ViboError):
         vb.kernels.encode(torch.zeros(4, 3, device="cuda"), torch.ones(4, 3, dtype=torch.uint8, device="cuda"),
                           big_d, conditional=False)
+
+
+@pytest.mark.parametrize("P,D,K", [(5000, 1, 2), (3001, 3, 1), (777, 8, 8), (1, 2, 3)])
+def test_flow_person_kernels_vs_torch(vb, P, D, K):
+    """vibo_flow_person_forward / _backward (draw + K planar flows + person-side terms of the
+    flow-form ELBO) against the same math in float64 PyTorch autograd (reference flows.py:21-41,
+    models.py:412-424 as restated in vibo_b200/flows.py)."""
+    from vibo_b200 import functional as VF
+    from vibo_b200.flows import NormalizingFlows
+    torch.manual_seed(P + D + K)
+    dev = "cuda"
+    flows = NormalizingFlows(D, n_flows=K).to(dev)
+    mu = (0.5 * torch.randn(P, D, device=dev)).requires_grad_()
+    lv = (0.3 * torch.randn(P, D, device=dev) - 1.0).requires_grad_()
+    eps = torch.randn(P, D, device=dev)
+    w_ll = torch.randn(P, D, device=dev)   # stands in for d LL / d theta_K
+    uhat, fw, fb = flows.stacked_parameters()
+    th0, thk, term = VF.FlowPerson.apply(mu, lv, eps, uhat, fw, fb)
+    loss = -((thk * w_ll).sum() + 0.7 * term)
+    loss.backward()
+    got = [mu.grad.clone(), lv.grad.clone()] + [p.grad.clone() for p in flows.parameters()]
+    # float64 reference
+    f64 = NormalizingFlows(D, n_flows=K).to(dev).double()
+    f64.load_state_dict({k: v.double() for k, v in flows.state_dict().items()})
+    mu2 = mu.detach().double().requires_grad_()
+    lv2 = lv.detach().double().requires_grad_()
+    e2 = eps.double()
+    t0 = e2 * torch.exp(0.5 * lv2) + mu2
+    tk, ldj = f64(t0)
+    c = 0.5 * np.log(2 * np.pi)
+    logp = (-0.5 * tk ** 2 - c).sum()
+    logq = (-(t0 - mu2) ** 2 / (2 * torch.exp(lv2)) - 0.5 * lv2 - c).sum()
+    term2 = logp - (logq - ldj.sum())
+    loss2 = -((tk * w_ll.double()).sum() + 0.7 * term2)
+    loss2.backward()
+    ref = [mu2.grad, lv2.grad] + [p.grad for p in f64.parameters()]
+    assert max_rel(th0.detach().cpu().numpy(), t0.detach().cpu().numpy()) < 1e-5
+    assert max_rel(thk.detach().cpu().numpy(), tk.detach().cpu().numpy()) < 1e-4
+    assert abs(term.item() - term2.item()) <= TOL * max(abs(term2.item()), 1.0)
+    for g, r in zip(got, ref):
+        assert rel_l2(g.cpu().numpy(), r.cpu().numpy()) < TOL, rel_l2(g.cpu().numpy(), r.cpu().numpy())

@@ -51,6 +51,8 @@ SIGNATURES = {
     "vibo_bernoulli_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_param_forward": (C.c_int, [_PD, C.c_int] + [_p] * 14),
     "vibo_param_backward": (C.c_int, [_PD, C.c_int] + [_p] * 18),
+    "vibo_flow_person_forward": (C.c_int, [_PD, C.c_int] + [_p] * 9 + [_p, C.c_size_t, _p]),
+    "vibo_flow_person_backward": (C.c_int, [_PD, C.c_int] + [_p] * 13 + [_p, C.c_size_t, _p]),
     "vibo_single_pass": (C.c_int, [_PD]),
     "vibo_launch_count": (C.c_uint64, []),
     "vibo_profile_begin": (C.c_int, []),

@@ -290,6 +290,61 @@ int vibo_bernoulli_loglik(const vibo_desc* desc, const float* response, const ui
   return VIBO_OK;
 }
 
+int vibo_flow_person_forward(const vibo_desc* desc, int n_flows, const float* ability_mu,
+                             const float* ability_logvar, const float* eps, const float* uhat,
+                             const float* w, const float* b, float* ability_0, float* ability_k,
+                             double* out_term, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (n_flows < 1 || n_flows > 8) return fail(VIBO_ERR_UNSUPPORTED, "n_flows must be in 1..8");
+  if (!ability_mu || !ability_logvar || !eps || !uhat || !w || !b || !ability_k || !out_term)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (workspace == nullptr || workspace_bytes < vibo_workspace_bytes(desc))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_workspace_bytes(desc)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (desc->num_person == 0) {
+    VIBO_CUDA(cudaMemsetAsync(out_term, 0, sizeof(double), st), "memset");
+    return VIBO_OK;
+  }
+  Carve ws(workspace, workspace_bytes);
+  double* part_term = ws.take<double>((size_t)vibo::sm_count() * 8 + 8);
+  VIBO_CUDA(vibo::launch_flow_person_forward(desc->num_person, desc->ability_dim, n_flows, ability_mu,
+                                             ability_logvar, eps, uhat, w, b, ability_0, ability_k, part_term,
+                                             out_term, st),
+            "flow_person_forward");
+  return VIBO_OK;
+}
+
+int vibo_flow_person_backward(const vibo_desc* desc, int n_flows, const float* ability_mu,
+                              const float* ability_logvar, const float* eps, const float* uhat,
+                              const float* w, const float* b, const float* g_ability_k,
+                              const float* g_term, float* g_ability_mu, float* g_ability_logvar,
+                              float* g_uhat, float* g_w, float* g_b, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (n_flows < 1 || n_flows > 8) return fail(VIBO_ERR_UNSUPPORTED, "n_flows must be in 1..8");
+  if (!ability_mu || !ability_logvar || !eps || !uhat || !w || !b || !g_ability_k || !g_term ||
+      !g_ability_mu || !g_ability_logvar || !g_uhat || !g_w || !g_b)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (workspace == nullptr || workspace_bytes < vibo_workspace_bytes(desc))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_workspace_bytes(desc)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = desc->ability_dim, n = n_flows * (2 * D + 1);
+  if (desc->num_person == 0) {
+    VIBO_CUDA(cudaMemsetAsync(g_uhat, 0, sizeof(float) * n_flows * D, st), "memset");
+    VIBO_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * n_flows * D, st), "memset");
+    VIBO_CUDA(cudaMemsetAsync(g_b, 0, sizeof(float) * n_flows, st), "memset");
+    return VIBO_OK;
+  }
+  Carve ws(workspace, workspace_bytes);
+  float* part_g = ws.take<float>((size_t)vibo::sm_count() * 8 * n);
+  if (!ws.ok()) return fail(VIBO_ERR_WORKSPACE, "workspace carve overflow");
+  VIBO_CUDA(vibo::launch_flow_person_backward(desc->num_person, D, n_flows, ability_mu, ability_logvar, eps,
+                                              uhat, w, b, g_ability_k, g_term, g_ability_mu, g_ability_logvar,
+                                              g_uhat, g_w, g_b, part_g, st),
+            "flow_person_backward");
+  return VIBO_OK;
+}
+
 int vibo_param_forward(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
                        const float* logvar_lookup, const float* eps_item, const float* w0,
                        const float* b0, const float* w2, const float* b2, const float* w4,

@@ -190,29 +190,47 @@ __global__ void __launch_bounds__(512) encode_bwd_kernel(int64_t P, int I, const
 // Reduce the per-CTA (A, B) partials in a fixed order and apply the expert
 // chain rule: d/d mu = tau A ; d/d lam = (mu A + B) (-exp(lam) tau^2).
 // Unconditional tables additionally sum over items.
-__global__ void encode_bwd_finalize_kernel(int I, int D, int cond, int nparts,
-                                           const float* __restrict__ part,
-                                           const float* __restrict__ table,
-                                           float* __restrict__ g_table) {
+__global__ void __launch_bounds__(256) encode_bwd_finalize_kernel(int I, int D, int cond, int nparts,
+                                                                  const float* __restrict__ part,
+                                                                  const float* __restrict__ table,
+                                                                  float* __restrict__ g_table) {
+  // block = 32 outputs x 8 slices of the partials, combined through shared memory in a fixed order
+  __shared__ double sa[8][33], sb[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int It = cond ? I : 1;
   const int n = 2 * It * D;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-    const int d = t % D, jt = (t / D) % It, r = t / (D * It);
-    double a = 0.0, b = 0.0;
+  const int t = blockIdx.x * 32 + lane;
+  double a = 0.0, b = 0.0;
+  int d = 0, jt = 0, r = 0;
+  if (t < n) {
+    d = t % D;
+    jt = (t / D) % It;
+    r = t / (D * It);
     const int j0 = cond ? jt : 0, j1 = cond ? jt + 1 : I;
-    for (int p = 0; p < nparts; ++p) {
+    for (int p = slice; p < nparts; p += 8) {
       const float* src = part + (size_t)p * 2 * I * 2 * D;
       for (int j = j0; j < j1; ++j) {
         a += src[((size_t)r * I + j) * 2 * D + d];
         b += src[((size_t)r * I + j) * 2 * D + D + d];
       }
     }
+  }
+  sa[slice][lane] = a;
+  sb[slice][lane] = b;
+  __syncthreads();
+  if (slice == 0 && t < n) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      ta += sa[q][lane];
+      tb += sb[q][lane];
+    }
     const float mu = table[((size_t)r * It + jt) * 2 * D + d];
     const float lam = table[((size_t)r * It + jt) * 2 * D + D + d];
     const float el = expf(lam);
     const float tau = 1.0f / (el + kPoeEps);
-    g_table[((size_t)r * It + jt) * 2 * D + d] = tau * (float)a;
-    g_table[((size_t)r * It + jt) * 2 * D + D + d] = (mu * (float)a + (float)b) * (-el * tau * tau);
+    g_table[((size_t)r * It + jt) * 2 * D + d] = tau * (float)ta;
+    g_table[((size_t)r * It + jt) * 2 * D + D + d] = (mu * (float)ta + (float)tb) * (-el * tau * tau);
   }
 }
 
@@ -335,24 +353,42 @@ __global__ void __launch_bounds__(512) link_kernel(int64_t P, int I, const float
   block_sum_to(ll_acc, part_ll + blockIdx.x);
 }
 
-// out[k] = scale * sum_p part[p][k], fixed order (deterministic).
-__global__ void sum_partials_f32_kernel(const float* __restrict__ part, int nparts, int n, float scale,
-                                        float* __restrict__ out) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * n + k];
-    out[k] = scale * (float)s;
+// out[k] = scale * sum_p part[p][k], fixed order (deterministic).  Block = 32 outputs x 8
+// slices: each thread sums every 8th partial, the slices are combined through shared memory.
+__global__ void __launch_bounds__(256) sum_partials_f32_kernel(const float* __restrict__ part, int nparts, int n,
+                                                               float scale, float* __restrict__ out) {
+  __shared__ double sh[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  double s = 0.0;
+  if (k < n)
+    for (int p = slice; p < nparts; p += 8) s += part[(size_t)p * n + k];
+  sh[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && k < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sh[q][lane];
+    out[k] = scale * (float)t;
   }
 }
 
-__global__ void sum_partials_f64_kernel(const double* __restrict__ part, int nparts, int stride,
-                                        int ncols, double* __restrict__ out) {
-  const int c = threadIdx.x;
-  if (c < ncols) {
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * stride + c];
-    out[c] = s;
+// out[c] = sum_p part[p * stride + c] for c < ncols: one block per column, strided partial
+// sums then a shared-memory tree in a fixed order.
+__global__ void __launch_bounds__(128) sum_partials_f64_kernel(const double* __restrict__ part, int nparts,
+                                                               int stride, int ncols, double* __restrict__ out) {
+  __shared__ double sh[128];
+  const int c = blockIdx.x;
+  double s = 0.0;
+  if (c < ncols)
+    for (int p = threadIdx.x; p < nparts; p += 128) s += part[(size_t)p * stride + c];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 64; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
   }
+  if (threadIdx.x == 0 && c < ncols) out[c] = sh[0];
 }
 
 // ---------------------------------------------------------------------------
@@ -465,7 +501,7 @@ static cudaError_t launch_encode_bwd_d(const vibo_desc& d, const float* resp, co
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int n = 2 * (d.conditional ? d.num_item : 1) * D;
-  encode_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(d.num_item, D, d.conditional, grid,
+  encode_bwd_finalize_kernel<<<(n + 31) / 32, 256, 0, st>>>(d.num_item, D, d.conditional, grid,
                                                               part, table, g_table);
   note_launch(2);
   return cudaGetLastError();
@@ -490,11 +526,11 @@ static cudaError_t launch_link_dm(const vibo_desc& d, const float* resp, const u
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+  sum_partials_f64_kernel<<<1, 128, 0, st>>>(part_ll, grid, 1, 1, out_ll);
   note_launch(2);
   if (g_item != nullptr) {
     const int n = d.num_item * F;
-    sum_partials_f32_kernel<<<(n + 127) / 128, 128, 0, st>>>(part_g, grid, n, 1.0f, g_item);
+    sum_partials_f32_kernel<<<(n + 31) / 32, 256, 0, st>>>(part_g, grid, n, 1.0f, g_item);
     note_launch();
   }
   return cudaGetLastError();
@@ -536,7 +572,7 @@ cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8
     if (e != cudaSuccess) return e;
     const int n = 2 * (d.conditional ? d.num_item : 1) * d.ability_dim;
     // the stream kernel already summed over items for the unconditional table
-    encode_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(d.conditional ? d.num_item : 1, d.ability_dim,
+    encode_bwd_finalize_kernel<<<(n + 31) / 32, 256, 0, st>>>(d.conditional ? d.num_item : 1, d.ability_dim,
                                                                 d.conditional, grid, part, table, g_table);
     note_launch(2);
     return cudaGetLastError();
@@ -557,11 +593,11 @@ cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* ma
                               &grid, st);
   if (e != cudaErrorNotSupported) {
     if (e != cudaSuccess) return e;
-    sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+    sum_partials_f64_kernel<<<1, 128, 0, st>>>(part_ll, grid, 1, 1, out_ll);
     note_launch(2);
     if (g_item != nullptr) {
       const int n = d.num_item * item_width_host(d.irt_model, d.ability_dim);
-      sum_partials_f32_kernel<<<(n + 127) / 128, 128, 0, st>>>(part_g, grid, n, 1.0f, g_item);
+      sum_partials_f32_kernel<<<(n + 31) / 32, 256, 0, st>>>(part_g, grid, n, 1.0f, g_item);
       note_launch();
     }
     return cudaGetLastError();
@@ -620,7 +656,7 @@ cudaError_t launch_bernoulli_ll(const vibo_desc& d, const float* resp, const uin
   bernoulli_ll_kernel<<<grid, 256, 0, st>>>(n, resp, mask, prob, part_ll, g_prob);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  sum_partials_f64_kernel<<<1, 32, 0, st>>>(part_ll, grid, 1, 1, out_ll);
+  sum_partials_f64_kernel<<<1, 128, 0, st>>>(part_ll, grid, 1, 1, out_ll);
   note_launch(2);
   return cudaGetLastError();
 }

@@ -57,6 +57,15 @@ cudaError_t launch_person_backward(const vibo_desc& d, float beta, const float* 
                                    const float* g_ll_ability, float* g_mu, float* g_lv,
                                    cudaStream_t st);
 cudaError_t launch_negate(float* v, int n, cudaStream_t st);
+int flow_grid(int64_t P);
+cudaError_t launch_flow_person_forward(int64_t P, int D, int K, const float* amu, const float* alv,
+                                       const float* eps, const float* uhat, const float* w, const float* b,
+                                       float* ability0, float* ability_k, double* part_term, double* out_term,
+                                       cudaStream_t st);
+cudaError_t launch_flow_person_backward(int64_t P, int D, int K, const float* amu, const float* alv,
+                                        const float* eps, const float* uhat, const float* w, const float* b,
+                                        const float* g_ability_k, const float* g_term, float* g_mu, float* g_lv,
+                                        float* g_uhat, float* g_w, float* g_b, float* part_g, cudaStream_t st);
 cudaError_t launch_accumulate(float* dst, const float* src, int n, double* dst2, const double* src2,
                               int n2, cudaStream_t st);
 

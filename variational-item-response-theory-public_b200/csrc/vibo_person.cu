@@ -53,12 +53,20 @@ __global__ void person_forward_kernel(int64_t P, int D, int form, int64_t person
   }
 }
 
-__global__ void sum_term_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int p = 0; p < n; ++p) s += part[p];
-    *out = s;
+// out = sum_p part[p]: 256 threads take strided partial sums, then a shared-memory tree in a
+// fixed order (deterministic).
+__global__ void __launch_bounds__(256) sum_term_kernel(const double* __restrict__ part, int n,
+                                                       double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int p = threadIdx.x; p < n; p += 256) s += part[p];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) *out = sh[0];
 }
 
 // d loss_k / d (ability_mu, ability_logvar) from d LL / d theta
@@ -122,7 +130,7 @@ cudaError_t launch_person_forward(const vibo_desc& d, const float* amu, const fl
                                               ability, part_term);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  sum_term_kernel<<<1, 32, 0, st>>>(part_term, grid, out_term);
+  sum_term_kernel<<<1, 256, 0, st>>>(part_term, grid, out_term);
   note_launch(2);
   return cudaGetLastError();
 }
@@ -135,6 +143,209 @@ cudaError_t launch_person_backward(const vibo_desc& d, float beta, const float* 
   person_backward_kernel<<<person_grid(n), 256, 0, st>>>(n, d.elbo_form, beta, amu, alv, eps, ability,
                                                          g_ll_ability, g_mu, g_lv);
   note_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Planar flows on the abilities (--n-norm-flows K; reference flows.py:21-41,58-66 and the
+// flow form of the ELBO, models.py:406-424), fused per person:
+//   theta_0 = mu + eps exp(lv / 2);  for k < K:  a = w_k . z + b_k, h = tanh(a),
+//   z <- z + uhat_k h,  ldj_k = log(|1 + (1 - h^2) (w_k . uhat_k)| + 1e-8)
+//   term_i = sum_d (-theta_K^2 / 2 + eps^2 / 2 + lv / 2) + sum_k ldj_k
+// which is  log N(theta_K; 0, 1) - log N(theta_0; mu, exp lv) + sum_k ldj_k  (the log 2 pi's cancel).
+// uhat (the invertibility-corrected u) is formed by the caller from (u, w): a handful of
+// parameter-only operations that stay in autograd.
+// ---------------------------------------------------------------------------
+constexpr int kFlowMaxK = 8, kFlowMaxD = 8;
+
+__device__ __forceinline__ void block_sum_to_p(double v, double* dst) {
+  __shared__ double s_part[32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) t += s_part[w2];
+    *dst = t;
+  }
+}
+
+__device__ __forceinline__ float flow_forward(int D, int K, const float* __restrict__ uhat,
+                                              const float* __restrict__ w, const float* __restrict__ b,
+                                              const float* wu, float* z, float (*zin)[kFlowMaxD], float* hs) {
+  float ldj = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    float a = b[k];
+    for (int d = 0; d < D; ++d) {
+      if (zin) zin[k][d] = z[d];
+      a = fmaf(w[k * D + d], z[d], a);
+    }
+    const float h = tanhf(a);
+    if (hs) hs[k] = h;
+    for (int d = 0; d < D; ++d) z[d] = fmaf(uhat[k * D + d], h, z[d]);
+    ldj += logf(fabsf(1.0f + (1.0f - h * h) * wu[k]) + 1e-8f);
+  }
+  return ldj;
+}
+
+__global__ void __launch_bounds__(256) flow_person_forward_kernel(int64_t P, int D, int K,
+                                                                  const float* __restrict__ amu,
+                                                                  const float* __restrict__ alv,
+                                                                  const float* __restrict__ eps,
+                                                                  const float* __restrict__ uhat,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ b,
+                                                                  float* __restrict__ ability0,
+                                                                  float* __restrict__ ability_k,
+                                                                  double* __restrict__ part_term) {
+  float wu[kFlowMaxK];
+  for (int k = 0; k < K; ++k) {
+    float v = 0.0f;
+    for (int d = 0; d < D; ++d) v = fmaf(w[k * D + d], uhat[k * D + d], v);
+    wu[k] = v;
+  }
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    float z[kFlowMaxD], term = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      const float lv = alv[i * D + d], e = eps[i * D + d];
+      z[d] = fmaf(e, expf(0.5f * lv), amu[i * D + d]);
+      if (ability0) ability0[i * D + d] = z[d];
+      term += 0.5f * e * e + 0.5f * lv;
+    }
+    term += flow_forward(D, K, uhat, w, b, wu, z, nullptr, nullptr);
+    for (int d = 0; d < D; ++d) {
+      ability_k[i * D + d] = z[d];
+      term -= 0.5f * z[d] * z[d];
+    }
+    acc += (double)term;
+  }
+  block_sum_to_p(acc, part_term + blockIdx.x);
+}
+
+// g_term: d loss / d (sum_i term_i) (device scalar); g_ability_k: d loss / d theta_K from the link.
+// part_g: [grid][K * (2 D + 1)] = (g_uhat | g_w | g_b) partial sums.
+__global__ void __launch_bounds__(256) flow_person_backward_kernel(int64_t P, int D, int K,
+                                                                   const float* __restrict__ amu,
+                                                                   const float* __restrict__ alv,
+                                                                   const float* __restrict__ eps,
+                                                                   const float* __restrict__ uhat,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ b,
+                                                                   const float* __restrict__ g_ability_k,
+                                                                   const float* __restrict__ g_term,
+                                                                   float* __restrict__ g_mu,
+                                                                   float* __restrict__ g_lv,
+                                                                   float* __restrict__ part_g) {
+  __shared__ float s_red[8];
+  const int NP = K * (2 * D + 1);
+  float wu[kFlowMaxK];
+  for (int k = 0; k < K; ++k) {
+    float v = 0.0f;
+    for (int d = 0; d < D; ++d) v = fmaf(w[k * D + d], uhat[k * D + d], v);
+    wu[k] = v;
+  }
+  const float c = g_term[0];
+  float gu[kFlowMaxK][kFlowMaxD], gw[kFlowMaxK][kFlowMaxD], gb[kFlowMaxK];
+  for (int k = 0; k < K; ++k) {
+    gb[k] = 0.0f;
+    for (int d = 0; d < D; ++d) gu[k][d] = gw[k][d] = 0.0f;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    float z[kFlowMaxD], zin[kFlowMaxK][kFlowMaxD], hs[kFlowMaxK], sd[kFlowMaxD], ev[kFlowMaxD];
+    for (int d = 0; d < D; ++d) {
+      sd[d] = expf(0.5f * alv[i * D + d]);
+      ev[d] = eps[i * D + d];
+      z[d] = fmaf(ev[d], sd[d], amu[i * D + d]);
+    }
+    flow_forward(D, K, uhat, w, b, wu, z, zin, hs);
+    float G[kFlowMaxD];
+    for (int d = 0; d < D; ++d) G[d] = g_ability_k[i * D + d] - c * z[d];   // d term / d theta_K = -theta_K
+    for (int k = K - 1; k >= 0; --k) {
+      const float h = hs[k], omh = 1.0f - h * h;
+      const float q = 1.0f + omh * wu[k];
+      const float dl = c * (q >= 0.0f ? 1.0f : -1.0f) / (fabsf(q) + 1e-8f);   // d loss / d s
+      float gdot = 0.0f;
+      for (int d = 0; d < D; ++d) gdot = fmaf(G[d], uhat[k * D + d], gdot);
+      const float ga = gdot * omh + dl * (-2.0f * h * omh) * wu[k];
+      for (int d = 0; d < D; ++d) {
+        gu[k][d] += G[d] * h + dl * omh * w[k * D + d];
+        gw[k][d] += ga * zin[k][d] + dl * omh * uhat[k * D + d];
+        G[d] = fmaf(ga, w[k * D + d], G[d]);
+      }
+      gb[k] += ga;
+    }
+    for (int d = 0; d < D; ++d) {
+      g_mu[i * D + d] = G[d];
+      g_lv[i * D + d] = 0.5f * G[d] * ev[d] * sd[d] + 0.5f * c;
+    }
+  }
+  // block sums of the parameter gradients, fixed order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = 0; n < NP; ++n) {
+    const int k = n / (2 * D + 1), r = n % (2 * D + 1);
+    float v = r < D ? gu[k][r] : (r < 2 * D ? gw[k][r - D] : gb[k]);
+    v = warp_sum(v);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int q = 0; q < 8; ++q) t += s_red[q];
+      part_g[(size_t)blockIdx.x * NP + n] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// out[k] = sum_p part[p][k] for the flow parameter gradients (n small), fixed order
+__global__ void flow_sum_kernel(const float* __restrict__ part, int nparts, int n, int D, int K,
+                                float* __restrict__ g_uhat, float* __restrict__ g_w, float* __restrict__ g_b) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * n + t];
+  const int k = t / (2 * D + 1), r = t % (2 * D + 1);
+  if (r < D) g_uhat[k * D + r] = (float)s;
+  else if (r < 2 * D) g_w[k * D + (r - D)] = (float)s;
+  else g_b[k] = (float)s;
+}
+
+int flow_grid(int64_t P) {
+  int64_t g = (P + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+cudaError_t launch_flow_person_forward(int64_t P, int D, int K, const float* amu, const float* alv,
+                                       const float* eps, const float* uhat, const float* w, const float* b,
+                                       float* ability0, float* ability_k, double* part_term, double* out_term,
+                                       cudaStream_t st) {
+  if (D > kFlowMaxD || K > kFlowMaxK || K < 1) return cudaErrorInvalidValue;
+  const int grid = flow_grid(P);
+  flow_person_forward_kernel<<<grid, 256, 0, st>>>(P, D, K, amu, alv, eps, uhat, w, b, ability0, ability_k,
+                                                   part_term);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sum_term_kernel<<<1, 256, 0, st>>>(part_term, grid, out_term);
+  note_launch(2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flow_person_backward(int64_t P, int D, int K, const float* amu, const float* alv,
+                                        const float* eps, const float* uhat, const float* w, const float* b,
+                                        const float* g_ability_k, const float* g_term, float* g_mu, float* g_lv,
+                                        float* g_uhat, float* g_w, float* g_b, float* part_g, cudaStream_t st) {
+  if (D > kFlowMaxD || K > kFlowMaxK || K < 1) return cudaErrorInvalidValue;
+  const int grid = flow_grid(P);
+  flow_person_backward_kernel<<<grid, 256, 0, st>>>(P, D, K, amu, alv, eps, uhat, w, b, g_ability_k, g_term, g_mu,
+                                                    g_lv, part_g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int n = K * (2 * D + 1);
+  flow_sum_kernel<<<(n + 127) / 128, 128, 0, st>>>(part_g, grid, n, D, K, g_uhat, g_w, g_b);
+  note_launch(2);
   return cudaGetLastError();
 }
 

@@ -203,7 +203,7 @@ BwdMmaPlan bwd_mma_plan(const vibo_desc& d) {
   const size_t row_bytes = (size_t)I * 5 + 4 * (size_t)D * 4;
   while ((size_t)(R + rq) * row_bytes <= 84 * 1024 && R + rq <= 64) R += rq;
   while (R > rq && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count()) R -= rq;
-  const size_t red = up((size_t)R * NC * 4 + 256, 128), info = 128;
+  const size_t red = up((size_t)2 * R * NC * 4 + 256, 128), info = 128;   // G tile double-buffered; 2 x 16 warp flags
   const size_t mask_off = (size_t)R * I * 4;
   const size_t parr_off = up(mask_off + (size_t)R * I, 16);
   const size_t stage = up(parr_off + 4 * (size_t)R * D * 4, 128);

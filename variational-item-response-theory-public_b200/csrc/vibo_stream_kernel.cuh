@@ -1130,8 +1130,9 @@ __global__ void __launch_bounds__(512) encode_bwd_mma_kernel(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int I = p.I, R = p.R, NS = p.NS;
-  float* Gs = cx.red;                                   // [R][NC] tf32 bit patterns
-  int* flag = reinterpret_cast<int*>(cx.info);          // [0]: stage has a missing cell
+  float* Gs0 = cx.red;                                  // [2][R][NC] tf32 bit patterns (double-buffered)
+  int* wflag = reinterpret_cast<int*>(cx.info);         // [2][16]: per-warp "saw a missing cell"
+  const int NWB = blockDim.x >> 5;
   float T1[MT][NT][4], To[MT][NT][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
@@ -1143,53 +1144,62 @@ __global__ void __launch_bounds__(512) encode_bwd_mma_kernel(const __grid_consta
   const int j0 = warp * 16 * MT;
 
   const int64_t n_chunks = (p.P + R - 1) / R, n_full = p.P / R;
-  int s = 0;
-  uint32_t phase = 0;
-  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
-    const int rows = (int)((p.P - c * R < R) ? p.P - c * R : R);
-    if (threadIdx.x == 0) flag[0] = 0;
-    if (c < n_full) {
-      mbar_wait(&cx.bar[s], phase);
+  // Stage prep (G tile as two TF32 terms + missing-cell flags) for the stage holding chunk c_;
+  // runs one stage AHEAD of the MMAs, so each stage costs a single CTA-wide barrier.
+  auto prep = [&](int64_t c_, int s_, uint32_t ph_, int buf_) {
+    unsigned char* st_ = cx.stages + (size_t)s_ * p.stage_bytes;
+    const int rows_ = (int)((p.P - c_ * R < R) ? p.P - c_ * R : R);
+    if (c_ < n_full) {
+      mbar_wait(&cx.bar[s_], ph_);
     } else {
-      stream_copy_ragged(p, c, st, rows);
+      stream_copy_ragged(p, c_, st_, rows_);
+      __syncthreads();
     }
-    __syncthreads();
-    const float* sx = reinterpret_cast<const float*>(st);
-    const uint8_t* sm = st + p.mask_off;
-    const float* s_mu = reinterpret_cast<const float*>(st + p.parr_off);
+    const uint8_t* sm_ = st_ + p.mask_off;
+    const float* s_mu = reinterpret_cast<const float*>(st_ + p.parr_off);
     const float* s_S = s_mu + (size_t)R * D;
     const float* s_gm = s_S + (size_t)R * D;
     const float* s_gl = s_gm + (size_t)R * D;
-    // ---- stage prep: G tile (two TF32 terms), missing-cell flag --------------
+    float* G = Gs0 + (size_t)buf_ * R * NC;
     for (int q = threadIdx.x; q < R * NC; q += blockDim.x) {
       const int r = q / NC, col = q % NC;
       float v = 0.0f;
-      if (r < rows && col < 4 * D) {
+      if (r < rows_ && col < 4 * D) {
         const int sp = col / (2 * D), k = col % (2 * D), d = k % D;
         const float sv = s_S[r * D + d], gm = s_gm[r * D + d];
         const float full = k < D ? gm / sv : -(gm * s_mu[r * D + d] + s_gl[r * D + d]) / sv;
         const float hi = tf32_round(full);
         v = sp == 0 ? hi : tf32_round(full - hi);
       }
-      Gs[q] = v;
+      G[q] = v;
     }
-    {
-      // any zero byte in the stage's mask block?  (16 bytes per load; mask bytes are 0 / 1)
-      bool miss = false;
-      const uint4* m4 = reinterpret_cast<const uint4*>(sm);
-      const int n16 = (rows * I) >> 4;
-      for (int k = threadIdx.x; k < n16; k += blockDim.x) {
-        const uint4 w = m4[k];
-        const uint32_t z = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
-                           ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
-        miss = miss || (z & 0x80808080u) != 0;
-      }
-      for (int k = (n16 << 4) + threadIdx.x; k < rows * I; k += blockDim.x) miss = miss || sm[k] == 0;
-      if (miss) flag[0] = 1;
+    // any zero byte in the stage's mask block?  (16 bytes per load; every warp reports)
+    bool miss = false;
+    const uint4* m4 = reinterpret_cast<const uint4*>(sm_);
+    const int n16 = (rows_ * I) >> 4;
+    for (int k = threadIdx.x; k < n16; k += blockDim.x) {
+      const uint4 w = m4[k];
+      const uint32_t z = ((w.x - 0x01010101u) & ~w.x) | ((w.y - 0x01010101u) & ~w.y) |
+                         ((w.z - 0x01010101u) & ~w.z) | ((w.w - 0x01010101u) & ~w.w);
+      miss = miss || (z & 0x80808080u) != 0;
     }
-    __syncthreads();
-    const bool has_missing = flag[0] != 0;
+    for (int k = (n16 << 4) + threadIdx.x; k < rows_ * I; k += blockDim.x) miss = miss || sm_[k] == 0;
+    miss = __any_sync(0xffffffffu, miss);
+    if (lane == 0) wflag[buf_ * 16 + warp] = miss ? 1 : 0;
+  };
+  prep(blockIdx.x, 0, 0, 0);
+  __syncthreads();
+
+  int s = 0, buf = 0;
+  uint32_t phase = 0;
+  for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    unsigned char* st = cx.stages + (size_t)s * p.stage_bytes;
+    const int rows = (int)((p.P - c * R < R) ? p.P - c * R : R);
+    const float* sx = reinterpret_cast<const float*>(st);
+    const uint8_t* sm = st + p.mask_off;
+    const float* Gs = Gs0 + (size_t)buf * R * NC;
+    bool has_missing = false;
+    for (int w2 = 0; w2 < NWB; ++w2) has_missing = has_missing || wflag[buf * 16 + w2] != 0;
     if (!has_missing && (int)threadIdx.x < NC) {
       float acc = 0.0f;
       for (int r = 0; r < rows; ++r) acc += Gs[r * NC + threadIdx.x];
@@ -1242,11 +1252,16 @@ __global__ void __launch_bounds__(512) encode_bwd_mma_kernel(const __grid_consta
         }
       }
     }
-    __syncthreads();   // every warp is done with stage s, Gs and flag
+    // prepare the NEXT stage of this CTA while slower warps finish their MMAs
+    const int64_t cnext = c + gridDim.x;
+    const int sn2 = s + 1 == NS ? 0 : s + 1;
+    if (cnext < n_chunks) prep(cnext, sn2, sn2 == 0 ? phase ^ 1u : phase, buf ^ 1);
+    __syncthreads();   // every warp is done with stage s and Gs[buf]; Gs[buf^1] / flags are ready
     if (threadIdx.x == 0) {
       const int64_t cn = c + (int64_t)NS * gridDim.x;
       if (cn < n_full) stream_issue(p, cn, st, &cx.bar[s]);
     }
+    buf ^= 1;
     if (++s == NS) {
       s = 0;
       phase ^= 1u;
@@ -1257,7 +1272,7 @@ __global__ void __launch_bounds__(512) encode_bwd_mma_kernel(const __grid_consta
   // TF32 terms are added and A^0 = A^obs - A^1.
   __syncthreads();
   float* tile = reinterpret_cast<float*>(cx.stages);
-  float* gf = Gs;   // [NC]
+  float* gf = Gs0;   // [NC]
   if ((int)threadIdx.x < NC) gf[threadIdx.x] = gfull;
   float* dst = part + (size_t)blockIdx.x * 2 * I * 2 * D;
 #pragma unroll

@@ -29,6 +29,12 @@ class PlanarFlow(nn.Module):
         return f_z, torch.log(torch.abs(1.0 + slope) + 1e-8)
 
 
+def planar_uhat(u, w):
+    """The invertibility-corrected u of a planar flow (reference flows.py:26-29)."""
+    uw = (u * w).sum()
+    return u + (F.softplus(uw) - 1.0 - uw) * w / (w * w).sum()
+
+
 class NormalizingFlows(nn.Module):
     """K planar flows in sequence; returns (z_K, sum_k log|det J_k|),
     reference flows.py:58-66."""
@@ -43,3 +49,10 @@ class NormalizingFlows(nn.Module):
             z, ldj = flow(z)
             total = total + ldj
         return z, total
+
+    def stacked_parameters(self):
+        """(uhat (K, D), w (K, D), b (K,)) for the fused per-person kernel."""
+        uhat = torch.stack([planar_uhat(f.u, f.w) for f in self.flows])
+        w = torch.stack([f.w for f in self.flows])
+        b = torch.cat([f.b for f in self.flows])
+        return uhat, w, b

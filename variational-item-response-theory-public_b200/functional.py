@@ -172,6 +172,34 @@ class LinkLogLik(torch.autograd.Function):
         return None, None, g * g_ab, g * g_it, None
 
 
+class FlowPerson(torch.autograd.Function):
+    """Reparameterised ability draw + K planar flows + the person-side terms of the
+    flow-form ELBO, one kernel each way (vibo_flow_person_forward / _backward).
+    Returns (ability_0, ability_K, term) with
+    term = sum_i [log N(theta_K; 0, 1) - log N(theta_0; mu, exp lv) + sum_k ldj_k]
+    (reference models.py:412-424, flows.py:21-41)."""
+
+    @staticmethod
+    def forward(ctx, ability_mu, ability_logvar, eps, uhat, w, b):
+        mu, lv, e = ability_mu.detach().contiguous(), ability_logvar.detach().contiguous(), eps.contiguous()
+        uh, ww, bb = uhat.detach().contiguous(), w.detach().contiguous(), b.detach().contiguous()
+        th0, thk, term = K.flow_person_forward(mu, lv, e, uh, ww, bb)
+        ctx.save_for_backward(mu, lv, e, uh, ww, bb)
+        ctx.mark_non_differentiable(th0)
+        return th0, thk, term[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, _g_th0, g_thk, g_term):
+        mu, lv, e, uh, ww, bb = ctx.saved_tensors
+        if g_thk is None:
+            g_thk = torch.zeros_like(mu)
+        if g_term is None:
+            g_term = torch.zeros((), device=mu.device)
+        g_mu, g_lv, g_uh, g_w, g_b = K.flow_person_backward(
+            mu, lv, e, uh, ww, bb, g_thk.contiguous().float(), g_term.reshape(1).float().contiguous())
+        return g_mu, g_lv, None, g_uh, g_w, g_b
+
+
 class Decode(torch.autograd.Function):
     """response_mu (P, I, 1) = irt_model_{1,2,3}pl(ability, item_feat)
     (vibo_decode).  API-parity path: the backward re-derives the link with

@@ -235,3 +235,47 @@ def param_backward(mu, lv, eps_item, w2, w4, hidden, g_table, g_item, g_term, *,
                                          *[_ptr(o) for o in outs], _stream(dev))
     _lib.check(rc, "vibo_param_backward")
     return outs
+
+
+def flow_person_forward(ability_mu, ability_logvar, eps, uhat, w, b):
+    """vibo_flow_person_forward -> (ability_0, ability_k (P, D), term f64 0-d)."""
+    lib = _lib.load()
+    if not ability_mu.is_cuda:
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    P, D = ability_mu.shape
+    K = uhat.shape[0]
+    dev = ability_mu.device
+    desc = make_desc(P, 1, D, 2, False)
+    th0 = torch.empty_like(ability_mu)
+    thk = torch.empty_like(ability_mu)
+    term = torch.empty(1, dtype=torch.float64, device=dev)
+    ws = workspace(desc, dev)
+    rc = lib.vibo_flow_person_forward(C.byref(desc), C.c_int(K), _ptr(ability_mu.contiguous()),
+                                      _ptr(ability_logvar.contiguous()), _ptr(eps.contiguous()),
+                                      _ptr(uhat.contiguous()), _ptr(w.contiguous()), _ptr(b.contiguous()),
+                                      _ptr(th0), _ptr(thk), _ptr(term), _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "vibo_flow_person_forward")
+    return th0, thk, term
+
+
+def flow_person_backward(ability_mu, ability_logvar, eps, uhat, w, b, g_ability_k, g_term):
+    """vibo_flow_person_backward -> (g_mu, g_logvar, g_uhat, g_w, g_b)."""
+    lib = _lib.load()
+    P, D = ability_mu.shape
+    K = uhat.shape[0]
+    dev = ability_mu.device
+    desc = make_desc(P, 1, D, 2, False)
+    g_mu = torch.empty_like(ability_mu)
+    g_lv = torch.empty_like(ability_mu)
+    g_uhat = torch.empty(K, D, dtype=torch.float32, device=dev)
+    g_w = torch.empty(K, D, dtype=torch.float32, device=dev)
+    g_b = torch.empty(K, dtype=torch.float32, device=dev)
+    ws = workspace(desc, dev)
+    rc = lib.vibo_flow_person_backward(C.byref(desc), C.c_int(K), _ptr(ability_mu.contiguous()),
+                                       _ptr(ability_logvar.contiguous()), _ptr(eps.contiguous()),
+                                       _ptr(uhat.contiguous()), _ptr(w.contiguous()), _ptr(b.contiguous()),
+                                       _ptr(g_ability_k.contiguous()), _ptr(g_term.contiguous()), _ptr(g_mu),
+                                       _ptr(g_lv), _ptr(g_uhat), _ptr(g_w), _ptr(g_b), _ptr(ws), ws.numel(),
+                                       _stream(dev))
+    _lib.check(rc, "vibo_flow_person_backward")
+    return g_mu, g_lv, g_uhat, g_w, g_b

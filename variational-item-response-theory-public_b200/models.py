@@ -24,7 +24,7 @@ from torch import nn
 from torch.nn import init
 
 from . import functional as VF
-from .flows import NormalizingFlows
+from .flows import NormalizingFlows, PlanarFlow
 
 LOG_SQRT_2PI = 0.5 * math.log(2.0 * math.pi)
 
@@ -345,12 +345,17 @@ class VIBO_1PL(nn.Module):
         if eps_ability is None:
             g = torch.Generator(device=resp.device).manual_seed(int(seed) + int(person_offset))
             eps_ability = torch.randn(a_mu.shape, generator=g, device=resp.device)
-        ability = eps_ability * torch.exp(0.5 * a_lv) + a_mu
-        ability_k, a_ldj = self.ability_norm_flows(ability)
         item_k, i_ldj = self.item_norm_flows(item_feat)
+        if resp.is_cuda and self.n_norm_flows <= 8 and isinstance(self.ability_norm_flows.flows[0], PlanarFlow):
+            # draw + K planar flows + person-side terms in one kernel each way
+            uhat, fw, fb = self.ability_norm_flows.stacked_parameters()
+            ability, ability_k, person = VF.FlowPerson.apply(a_mu, a_lv, eps_ability, uhat, fw, fb)
+        else:
+            ability = eps_ability * torch.exp(0.5 * a_lv) + a_mu
+            ability_k, a_ldj = self.ability_norm_flows(ability)
+            person = standard_normal_log_pdf(ability_k).sum() \
+                - (normal_log_pdf(ability, a_mu, a_lv).sum() - a_ldj.sum())
         ll = VF.LinkLogLik.apply(resp, msk, ability_k, item_k, self.irt_num)
-        person = standard_normal_log_pdf(ability_k).sum() \
-            - (normal_log_pdf(ability, a_mu, a_lv).sum() - a_ldj.sum())
         item = standard_normal_log_pdf(item_k).sum() \
             - (normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum() - i_ldj.sum())
         loss = -(ll + person + item_term_scale * item)
