@@ -27,10 +27,16 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   if (off != nullptr && off[0] == '1') return pl;
   // items per lane: the register budget of the lane-owned state bounds M
   int M = I <= 512 ? 1 : (I <= 1024 ? 2 : 4);
-  if (kind == 1 && M == 1) M = 2;   // the link kernel works on f32x2 pairs of items
   if (I > 2048) return pl;
   const int F = d.irt_model == 1 ? 1 : (d.irt_model == 2 ? D + 1 : D + 2);
   const int regs = kind == 0 ? (d.conditional ? 4 * D : 0) : (kind == 1 ? 2 * F + 2 : 4 * D);
+  if (kind == 1) {
+    // the link kernel works on f32x2 pairs of items; 4 items per lane halve the share of the
+    // per-row overhead (theta loads, transpose-reduce) when the lane-owned state still fits
+    const char* m4 = getenv("VIBO_LINK_M");
+    const int want = m4 != nullptr ? atoi(m4) : 4;
+    M = (want >= 4 && 4 * regs <= 64 && I > 256) ? 4 : (M < 2 ? 2 : M);
+  }
   if (M * regs > 64) return pl;   // beyond this the lane-owned state spills
   const int NW = (I + 32 * M - 1) / (32 * M);
   // rows per stage: a multiple of (a) the alignment quantum of the bulk copies
