@@ -89,6 +89,35 @@ def product_of_experts(mu: Tensor, logvar: Tensor, eps: float = 1e-8):
     return pd_mu, torch.log(pd_var)
 
 
+def ability_posterior_mean(p: Params, response: Tensor, mask: Tensor, item_feat: Optional[Tensor],
+                           ability_dim: int):
+    """Per-cell encoder + mean merge: models.py:584-594 (``mlp1`` / ``mlp2``), :631-650
+    (``_forward_mean`` incl. the per-person loop over observed cells when anything is missing)."""
+    P, I, _ = response.shape
+    flat = response.reshape(P * I, 1)
+    if item_feat is not None:
+        tiled = item_feat.unsqueeze(0).repeat(P, 1, 1).reshape(P * I, item_feat.shape[1])
+        flat = torch.cat([flat, tiled], dim=1)
+    h = F.elu(F.linear(flat, p["ability_encoder.mlp1.0.weight"], p["ability_encoder.mlp1.0.bias"]))
+    h = F.linear(h, p["ability_encoder.mlp1.2.weight"], p["ability_encoder.mlp1.2.bias"])
+    hid = F.elu(h).reshape(P, I, -1)
+    H = hid.shape[2]
+    has_missing = bool(torch.sum(1 - mask).item())
+    if has_missing:
+        rows = []
+        for i in range(P):
+            keep = mask[i].repeat(1, H).bool()
+            n_i = int(mask[i].squeeze().sum().item())
+            rows.append(hid[i][keep].view(n_i, H).mean(0))
+        hid_mean = torch.stack(rows)
+    else:
+        hid_mean = hid.mean(1)
+    o = F.elu(F.linear(hid_mean, p["ability_encoder.mlp2.0.weight"], p["ability_encoder.mlp2.0.bias"]))
+    o = F.linear(o, p["ability_encoder.mlp2.2.weight"], p["ability_encoder.mlp2.2.bias"])
+    mu, logvar = torch.chunk(o, 2, dim=1)
+    return mu, logvar
+
+
 def ability_posterior(p: Params, response: Tensor, mask: Tensor, item_feat: Optional[Tensor],
                       ability_dim: int, replace_missing_with_prior: bool = True):
     """Per-cell encoder + product merge.
@@ -196,8 +225,11 @@ def forward(p: Params, response: Tensor, mask: Tensor, eps_item: Tensor, eps_abi
     item_mu = p["item_encoder.mu_lookup.weight"]
     item_lv = p["item_encoder.logvar_lookup.weight"]
     item_feat = reparameterize(item_mu, item_lv, eps_item)
-    a_mu, a_lv = ability_posterior(p, response, mask, item_feat if conditional else None,
-                                   ability_dim, replace_missing_with_prior)
+    if "ability_encoder.mlp1.0.weight" in p:   # --ability-merge mean
+        a_mu, a_lv = ability_posterior_mean(p, response, mask, item_feat if conditional else None, ability_dim)
+    else:
+        a_mu, a_lv = ability_posterior(p, response, mask, item_feat if conditional else None,
+                                       ability_dim, replace_missing_with_prior)
     ability = reparameterize(a_mu, a_lv, eps_ability)
     out = dict(ability=ability, ability_mu=a_mu, ability_logvar=a_lv,
                item_feat=item_feat, item_feat_mu=item_mu, item_feat_logvar=item_lv)

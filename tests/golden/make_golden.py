@@ -65,10 +65,10 @@ CASES = []
 
 
 def case(name, irt, D, cond, P, I, missing=0.0, drop=False, beta=1.0, use_kl=True,
-         flows=0, trained_like=False, seed=0):
+         flows=0, trained_like=False, seed=0, merge="product"):
     CASES.append(dict(name=name, irt_model=irt, ability_dim=D, conditional=cond, P=P, I=I,
                       missing_frac=missing, drop_missing=drop, beta=beta, use_kl=use_kl,
-                      n_flows=flows, trained_like=trained_like, seed=seed))
+                      n_flows=flows, trained_like=trained_like, seed=seed, merge=merge))
 
 
 # --- the grid (small enough that the whole CPU suite stays in seconds) -----
@@ -92,6 +92,17 @@ case("m1pl_d2_unc_flows1", 1, 2, False, 17, 12, flows=1, use_kl=False, seed=207)
 case("m3pl_d5_cond_trained", 3, 5, True, 32, 24, trained_like=True, seed=208)
 case("m2pl_d1_unc_wide", 2, 1, False, 9, 140, seed=209)
 case("m2pl_d1_unc_saturating", 2, 1, False, 16, 12, seed=210)
+# --ability-merge mean (the constructor default of the reference; models.py:584-594, 631-650).
+# The mean-merge posterior at fresh init is wide (sd ~ 1), which with N(0,1) item features puts
+# logits in the 12..16 band where the fp32 reference is its own noise ("knife-edge"):
+# the cases use the trained-like item state.
+case("m2pl_d1_unc_mean_full", 2, 1, False, 24, 20, merge="mean", trained_like=True, seed=301)
+case("m2pl_d2_unc_mean_miss", 2, 2, False, 19, 17, missing=0.15, beta=0.7, merge="mean", trained_like=True, seed=302)
+case("m3pl_d2_cond_mean_full", 3, 2, True, 22, 18, merge="mean", trained_like=True, seed=303)
+case("m1pl_d3_cond_mean_miss", 1, 3, True, 20, 15, missing=0.2, use_kl=False, merge="mean", trained_like=True,
+     seed=304)
+case("m2pl_d1_unc_mean_flows2", 2, 1, False, 18, 14, flows=2, use_kl=False, merge="mean", trained_like=True,
+     seed=305)
 
 
 def run_case(models, c):
@@ -99,7 +110,7 @@ def run_case(models, c):
     P, I = c["P"], c["I"]
     cls = {1: models.VIBO_1PL, 2: models.VIBO_2PL, 3: models.VIBO_3PL}[irt]
     torch.manual_seed(c["seed"])
-    model = cls(D, I, hidden_dim=64, ability_merge="product", conditional_posterior=cond,
+    model = cls(D, I, hidden_dim=64, ability_merge=c.get("merge", "product"), conditional_posterior=cond,
                 generative_model="irt", response_dist="bernoulli",
                 replace_missing_with_prior=not c["drop_missing"], n_norm_flows=c["n_flows"])
     init_state = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
@@ -235,13 +246,19 @@ def run_mask_fixture():
 def main():
     models = _import_reference()
     index = []
+    regenerate_all = "--all" in sys.argv   # default: only cases whose fixture file is missing
     for c in CASES:
-        rec = run_case(models, c)
-        np.savez_compressed(os.path.join(HERE, c["name"] + ".npz"), **rec)
         index.append(c)
+        path = os.path.join(HERE, c["name"] + ".npz")
+        if os.path.exists(path) and not regenerate_all:
+            continue
+        rec = run_case(models, c)
+        np.savez_compressed(path, **rec)
         print(f"{c['name']:40s} loss={float(rec['loss']):.6f}")
-    np.savez_compressed(os.path.join(HERE, "log_marginal_2pl_d2.npz"), **run_log_marginal(models))
-    np.savez_compressed(os.path.join(HERE, "artificial_mask.npz"), **run_mask_fixture())
+    if regenerate_all or not os.path.exists(os.path.join(HERE, "log_marginal_2pl_d2.npz")):
+        np.savez_compressed(os.path.join(HERE, "log_marginal_2pl_d2.npz"), **run_log_marginal(models))
+    if regenerate_all or not os.path.exists(os.path.join(HERE, "artificial_mask.npz")):
+        np.savez_compressed(os.path.join(HERE, "artificial_mask.npz"), **run_mask_fixture())
     with open(os.path.join(HERE, "index.json"), "w") as f:
         json.dump(dict(torch=torch.__version__, reference=REF, cases=index), f, indent=1)
 

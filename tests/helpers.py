@@ -45,7 +45,7 @@ def build_model(cfg, params, device="cpu"):
     """Drop-in module with the fixture's parameters loaded."""
     import vibo_b200
     cls = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[cfg["irt_model"]]
-    model = cls(cfg["ability_dim"], cfg["I"], hidden_dim=64, ability_merge="product",
+    model = cls(cfg["ability_dim"], cfg["I"], hidden_dim=64, ability_merge=cfg.get("merge", "product"),
                 conditional_posterior=cfg["conditional"],
                 replace_missing_with_prior=not cfg["drop_missing"], n_norm_flows=cfg["n_flows"])
     missing, unexpected = model.load_state_dict(params, strict=True)

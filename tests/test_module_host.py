@@ -131,8 +131,9 @@ def test_item_kl_charged_in_full_per_batch():
 
 def test_unsupported_options_raise():
     import vibo_b200
-    with pytest.raises(NotImplementedError):
-        vibo_b200.VIBO_2PL(1, 5)  # class default ability_merge='mean'
+    m = vibo_b200.VIBO_2PL(1, 5)  # class default ability_merge='mean' (reference models.py:252)
+    assert sorted(k for k in m.state_dict() if k.startswith("ability_encoder")) == sorted(
+        f"ability_encoder.{n}.{i}.{w}" for n in ("mlp1", "mlp2") for i in (0, 2) for w in ("weight", "bias"))
     with pytest.raises(NotImplementedError):
         vibo_b200.VIBO_2PL(1, 5, ability_merge="product", generative_model="deep")
     with pytest.raises(AssertionError):

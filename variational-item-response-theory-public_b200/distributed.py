@@ -60,7 +60,8 @@ class ShardedElboTrainer:
         m = self.model
         d = _lib.Desc(1 << 20, m.num_item, m.ability_dim, m.irt_num, int(m.conditional_posterior), 0, 0, 0)
         import ctypes
-        return m.n_norm_flows == 0 and bool(_lib.load().vibo_single_pass(ctypes.byref(d)))
+        return (m.n_norm_flows == 0 and m.ability_merge == 'product'
+                and bool(_lib.load().vibo_single_pass(ctypes.byref(d))))
 
     # ---------------------------------------------------------------- pieces
     def _loss(self, response, mask, seed):

@@ -20,6 +20,7 @@ from __future__ import annotations
 import math
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 from torch.nn import init
 
@@ -39,28 +40,82 @@ def _encoder_mlp(input_dim, hidden_dim, output_dim):
     )
 
 
+def _mean_mlps(input_dim, hidden_dim, output_dim):
+    """reference models.py:584-594 (``_create_models_mean``): mlp1 then mlp2."""
+    mlp1 = nn.Sequential(nn.Linear(input_dim, hidden_dim), nn.ELU(inplace=True),
+                         nn.Linear(hidden_dim, hidden_dim))
+    mlp2 = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.ELU(inplace=True),
+                         nn.Linear(hidden_dim, output_dim))
+    return mlp1, mlp2
+
+
 class AbilityInferenceNetwork(nn.Module):
-    """q(ability | responses): per-cell Gaussian experts merged by a product
-    of experts (reference models.py:551-661).  Holds ``self.mlp`` with the
-    reference's ``state_dict`` keys (``mlp.{0,2,4}.{weight,bias}``)."""
+    """q(ability | responses) (reference models.py:551-661).
+
+    ``product`` (the vibo.py default): per-cell Gaussian experts merged by a product of
+    experts; holds ``self.mlp`` (``mlp.{0,2,4}.{weight,bias}``) and runs on the encode kernels.
+    ``mean`` (the constructor default of the reference): per-cell hidden vectors averaged over a
+    person's observed items, then a second MLP (``mlp1.{0,2}``, ``mlp2.{0,2}``).  For 0/1
+    responses the per-cell MLP collapses to a table exactly as for ``product``, so the average
+    is ``(counts or indicator matrix) x table`` -- composed from PyTorch reductions / GEMMs
+    around the link kernel (no per-cell activations are ever materialised)."""
 
     conditional = False
 
     def __init__(self, ability_dim, response_dim, hidden_dim=64, ability_merge='mean',
                  replace_missing_with_prior=True):
         super().__init__()
-        if ability_merge != 'product':
-            raise NotImplementedError(
-                "only ability_merge='product' (the vibo.py default) runs on the B200 kernels; "
-                "'mean' is listed as a next step in DESIGN.md")
+        assert ability_merge in ('mean', 'product')
         self.ability_dim = ability_dim
         self.response_dim = response_dim
         self.hidden_dim = hidden_dim
         self.ability_merge = ability_merge
         self.replace_missing_with_prior = replace_missing_with_prior
-        self.mlp = _encoder_mlp(response_dim, hidden_dim, ability_dim * 2)
+        self._create_models(response_dim)
         # the two possible cell inputs; non-persistent so state_dict keys stay the reference's
         self.register_buffer("_cell_inputs", torch.tensor([[0.0], [1.0]]), persistent=False)
+
+    def _create_models(self, input_dim):
+        if self.ability_merge == 'product':
+            self.mlp = _encoder_mlp(input_dim, self.hidden_dim, self.ability_dim * 2)
+        else:
+            self.mlp1, self.mlp2 = _mean_mlps(input_dim, self.hidden_dim, self.ability_dim * 2)
+
+    def _cell_rows(self, item_feat):
+        """The distinct per-cell MLP inputs: (2, 1) unconditional, (2 I, 1 + F) conditional."""
+        if not self.conditional:
+            return self._cell_inputs.to(self._first_weight().dtype), 1
+        I = item_feat.shape[0]
+        r = self._cell_inputs.to(item_feat.dtype).view(2, 1, 1).expand(2, I, 1)
+        rows = torch.cat([r, item_feat.unsqueeze(0).expand(2, I, -1)], dim=2)
+        return rows.reshape(2 * I, -1), I
+
+    def _first_weight(self):
+        return self.mlp[0].weight if self.ability_merge == 'product' else self.mlp1[0].weight
+
+    def _forward_mean(self, resp, msk, item_feat):
+        """reference models.py:631-650 with the table collapse: hidden table (2, It, H), per-person
+        masked mean over items, mlp2.  resp (P, I) f32, msk (P, I) u8."""
+        rows, It = self._cell_rows(item_feat)
+        hid = F.elu(self.mlp1(rows)).reshape(2, It, self.hidden_dim)
+        obs = msk != 0
+        one = (resp > 0.5) & obs
+        n_obs = obs.sum(1, keepdim=True).to(hid.dtype)
+        if It == 1:
+            n1 = one.sum(1, keepdim=True).to(hid.dtype)
+            hid_sum = (n_obs - n1) * hid[0] + n1 * hid[1]
+        else:
+            hid_sum = torch.zeros(resp.shape[0], self.hidden_dim, dtype=hid.dtype, device=hid.device)
+            blk = 32768   # bounds the (rows, I) indicator temporaries
+            parts = []
+            for a in range(0, resp.shape[0], blk):
+                w1 = one[a:a + blk].to(hid.dtype)
+                w0 = obs[a:a + blk].to(hid.dtype) - w1
+                parts.append(w1 @ hid[1] + w0 @ hid[0])
+            hid_sum = torch.cat(parts) if parts else hid_sum
+        hid_mean = hid_sum / n_obs
+        mu, logvar = torch.chunk(self.mlp2(hid_mean), 2, dim=1)
+        return mu, logvar
 
     @property
     def missing_policy(self):
@@ -72,6 +127,8 @@ class AbilityInferenceNetwork(nn.Module):
 
     def forward(self, response, mask, item_feat=None):
         resp, msk = VF.prepare_rows(response, mask)
+        if self.ability_merge == 'mean':
+            return self._forward_mean(resp, msk, item_feat)
         table = self.expert_table(item_feat)
         return VF.EncodePosterior.apply(resp, msk, table, self.conditional, self.missing_policy)
 
@@ -91,7 +148,7 @@ class ConditionalAbilityInferenceNetwork(AbilityInferenceNetwork):
                          ability_merge=ability_merge,
                          replace_missing_with_prior=replace_missing_with_prior)
         self.item_feat_dim = item_feat_dim
-        self.mlp = _encoder_mlp(response_dim + item_feat_dim, hidden_dim, ability_dim * 2)
+        self._create_models(response_dim + item_feat_dim)
 
     def expert_table(self, item_feat=None):
         """(2, I, 2D): the MLP on [r, item_feat_j] for r = 0, 1 and every item."""
@@ -279,14 +336,21 @@ class VIBO_1PL(nn.Module):
         item_feat_mu, item_feat_logvar = self.item_encoder()
         host_rows = (not resp.is_cuda) and item_feat_mu.is_cuda
         if host_rows:
-            if self.n_norm_flows > 0 or return_outputs:
-                raise NotImplementedError("host-resident rows: flows / return_outputs need device rows")
+            if self.n_norm_flows > 0 or return_outputs or self.ability_merge == 'mean':
+                raise NotImplementedError("host-resident rows: flows / mean merge / return_outputs need device rows")
             if eps_ability is None and seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         if eps_item is None:
             eps_item = torch.randn_like(item_feat_mu)
         kl_form = bool(use_kl_divergence)
         # unconditional model on the GPU: the whole parameter-side chain is two small kernels
+        if self.ability_merge == 'mean':
+            item_feat = eps_item * torch.exp(0.5 * item_feat_logvar) + item_feat_mu
+            if eps_ability is None:
+                eps_ability = torch.randn(P, self.ability_dim, dtype=torch.float32, device=resp.device)
+            return self._composed_elbo(resp, msk, None, item_feat, item_feat_mu, item_feat_logvar, eps_ability,
+                                       seed, person_offset, item_term_scale, return_outputs,
+                                       float(annealing_factor), kl_form)
         chain = (self.fuse_param_chain and item_feat_mu.is_cuda and not self.conditional_posterior
                  and self.n_norm_flows == 0 and self.hidden_dim <= 256)
         if chain:
@@ -303,8 +367,9 @@ class VIBO_1PL(nn.Module):
         beta = float(annealing_factor)
 
         if self.n_norm_flows > 0:
-            return self._flow_elbo(resp, msk, table, item_feat, item_feat_mu, item_feat_logvar,
-                                   eps_ability, seed, person_offset, item_term_scale, return_outputs)
+            return self._composed_elbo(resp, msk, table, item_feat, item_feat_mu, item_feat_logvar,
+                                       eps_ability, seed, person_offset, item_term_scale, return_outputs,
+                                       beta, kl_form)
 
         cfg = dict(irt_model=self.irt_num, conditional=self.conditional_posterior,
                    missing_policy=self.ability_encoder.missing_policy,
@@ -335,34 +400,53 @@ class VIBO_1PL(nn.Module):
                               item_feat_logvar=item_feat_logvar)
         return loss
 
-    def _flow_elbo(self, resp, msk, table, item_feat, item_feat_mu, item_feat_logvar, eps_ability,
-                   seed, person_offset, item_term_scale, return_outputs):
-        """Flow form (reference models.py:406-424): encode kernel -> planar
-        flows in autograd -> link/log-likelihood kernel.  annealing_factor is
-        ignored exactly as in the reference."""
+    def _composed_elbo(self, resp, msk, table, item_feat, item_feat_mu, item_feat_logvar, eps_ability,
+                       seed, person_offset, item_term_scale, return_outputs, beta, kl_form):
+        """-ELBO composed in autograd around the kernels: ability posterior (encode kernel for the
+        product merge, PyTorch reductions / GEMMs on the collapsed table for the mean merge) ->
+        draw [-> planar flows, fused per person on the GPU] -> link / log-likelihood kernel ->
+        prior terms.  Used for --n-norm-flows (reference models.py:406-424, where
+        annealing_factor is ignored exactly as in the reference) and --ability-merge mean."""
         enc = self.ability_encoder
-        a_mu, a_lv = VF.EncodePosterior.apply(resp, msk, table, enc.conditional, enc.missing_policy)
+        if self.ability_merge == 'mean':
+            a_mu, a_lv = enc._forward_mean(resp, msk, item_feat if self.conditional_posterior else None)
+        else:
+            a_mu, a_lv = VF.EncodePosterior.apply(resp, msk, table, enc.conditional, enc.missing_policy)
         if eps_ability is None:
             g = torch.Generator(device=resp.device).manual_seed(int(seed) + int(person_offset))
             eps_ability = torch.randn(a_mu.shape, generator=g, device=resp.device)
-        item_k, i_ldj = self.item_norm_flows(item_feat)
-        if resp.is_cuda and self.n_norm_flows <= 8 and isinstance(self.ability_norm_flows.flows[0], PlanarFlow):
-            # draw + K planar flows + person-side terms in one kernel each way
-            uhat, fw, fb = self.ability_norm_flows.stacked_parameters()
-            ability, ability_k, person = VF.FlowPerson.apply(a_mu, a_lv, eps_ability, uhat, fw, fb)
+        outputs = dict(ability_mu=a_mu, ability_logvar=a_lv, item_feat=item_feat, item_feat_mu=item_feat_mu,
+                       item_feat_logvar=item_feat_logvar)
+        if self.n_norm_flows > 0:
+            item_k, i_ldj = self.item_norm_flows(item_feat)
+            if resp.is_cuda and self.n_norm_flows <= 8 and isinstance(self.ability_norm_flows.flows[0], PlanarFlow):
+                # draw + K planar flows + person-side terms in one kernel each way
+                uhat, fw, fb = self.ability_norm_flows.stacked_parameters()
+                ability, ability_k, person = VF.FlowPerson.apply(a_mu, a_lv, eps_ability, uhat, fw, fb)
+            else:
+                ability = eps_ability * torch.exp(0.5 * a_lv) + a_mu
+                ability_k, a_ldj = self.ability_norm_flows(ability)
+                person = standard_normal_log_pdf(ability_k).sum() \
+                    - (normal_log_pdf(ability, a_mu, a_lv).sum() - a_ldj.sum())
+            ll = VF.LinkLogLik.apply(resp, msk, ability_k, item_k, self.irt_num)
+            item = standard_normal_log_pdf(item_k).sum() \
+                - (normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum() - i_ldj.sum())
+            loss = -(ll + person + item_term_scale * item)
+            outputs.update(ability=ability, ability_k=ability_k, item_feat_k=item_k)
         else:
             ability = eps_ability * torch.exp(0.5 * a_lv) + a_mu
-            ability_k, a_ldj = self.ability_norm_flows(ability)
-            person = standard_normal_log_pdf(ability_k).sum() \
-                - (normal_log_pdf(ability, a_mu, a_lv).sum() - a_ldj.sum())
-        ll = VF.LinkLogLik.apply(resp, msk, ability_k, item_k, self.irt_num)
-        item = standard_normal_log_pdf(item_k).sum() \
-            - (normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum() - i_ldj.sum())
-        loss = -(ll + person + item_term_scale * item)
+            ll = VF.LinkLogLik.apply(resp, msk, ability, item_feat, self.irt_num)
+            if kl_form:
+                person = -beta * kl_divergence_standard_normal_prior(a_mu, a_lv).sum()
+                item = -beta * kl_divergence_standard_normal_prior(item_feat_mu, item_feat_logvar).sum()
+            else:
+                person = standard_normal_log_pdf(ability).sum() - normal_log_pdf(ability, a_mu, a_lv).sum()
+                item = standard_normal_log_pdf(item_feat).sum() \
+                    - normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum()
+            loss = -(ll + person + item_term_scale * item)
+            outputs.update(ability=ability)
         if return_outputs:
-            return loss, dict(ability=ability, ability_mu=a_mu, ability_logvar=a_lv, ability_k=ability_k,
-                              item_feat=item_feat, item_feat_k=item_k, item_feat_mu=item_feat_mu,
-                              item_feat_logvar=item_feat_logvar)
+            return loss, outputs
         return loss
 
 
