@@ -220,7 +220,7 @@ def main():
     ap.add_argument("--mode", default="eval", choices=["train", "eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra-workloads", default="c3,c5",
+    ap.add_argument("--extra-workloads", default="c2,c3,c5",
                     help="other BASELINE.json configs timed after the headline at N=1 (comma list, '' = none)")
     ap.add_argument("--cuda-graph", type=int, default=1, help="capture the step in a CUDA graph (1/0)")
     args = ap.parse_args()
