@@ -153,6 +153,13 @@ int vibo_link_loglik(const vibo_desc* desc, const float* response, const uint8_t
                      float* g_ability, float* g_item, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Per-person sufficient statistics of an unconditional encoder: counts (P, 2) =
+ * (number of observed responses equal to 1, number of observed responses).  The masked mean
+ * of `--ability-merge mean` (models.py:631-650) and the unconditional product of experts
+ * (models.py:596-629) depend on a row only through these counts. */
+int vibo_person_counts(const vibo_desc* desc, const float* response, const uint8_t* mask, float* counts,
+                       void* stream);
+
 /* decode: response_mu (P, I) = irt_model_{1,2,3}pl(ability, item_feat),
  * models.py:729-766 (API-parity path; the fused entry never needs it). */
 int vibo_decode(const vibo_desc* desc, const float* ability, const float* item_feat,

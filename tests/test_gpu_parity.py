@@ -346,3 +346,19 @@ def test_flow_person_kernels_vs_torch(vb, P, D, K):
     assert abs(term.item() - term2.item()) <= TOL * max(abs(term2.item()), 1.0)
     for g, r in zip(got, ref):
         assert rel_l2(g.cpu().numpy(), r.cpu().numpy()) < TOL, rel_l2(g.cpu().numpy(), r.cpu().numpy())
+
+
+@pytest.mark.parametrize("P,I,missing,offset", [(5000, 100, 0.1, 0), (3001, 95, 0.2, 0), (2000, 1000, 0.0, 0),
+                                                (777, 333, 0.3, 1), (100, 2500, 0.1, 0)])
+def test_person_counts_kernel(vb, P, I, missing, offset):
+    """vibo_person_counts (stream kernel; warp-per-row fallback for unaligned sub-views and
+    I > 2048) against plain PyTorch integer reductions: bit-exact."""
+    g = torch.Generator(device="cuda").manual_seed(P + I)
+    resp = (torch.rand(P + offset, I, generator=g, device="cuda") < 0.4).float()
+    mask = (torch.rand(P + offset, I, generator=g, device="cuda") >= missing).to(torch.uint8)
+    resp[mask == 0] = -1.0
+    r, m = resp[offset:], mask[offset:]          # offset = 1 row: pointers lose their 16-byte alignment
+    counts = vb.kernels.person_counts(r, m)
+    obs = m != 0
+    ref = torch.stack([((r > 0.5) & obs).sum(1), obs.sum(1)], 1).float()
+    assert torch.equal(counts, ref)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "vibo_fused_elbo_host": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_uint64, C.c_float, _p, _p, _p, _p,
                                        C.c_int64, _p, C.c_size_t, _p, C.c_size_t, _p]),
     "vibo_encode": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p]),
+    "vibo_person_counts": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_encode_backward": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_link_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_decode": (C.c_int, [_PD, _p, _p, _p, _p]),

@@ -201,6 +201,16 @@ int vibo_encode(const vibo_desc* desc, const float* response, const uint8_t* mas
   return VIBO_OK;
 }
 
+int vibo_person_counts(const vibo_desc* desc, const float* response, const uint8_t* mask, float* counts,
+                       void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!response || !mask || !counts) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (desc->num_person == 0) return VIBO_OK;
+  VIBO_CUDA(vibo::launch_person_counts(*desc, response, mask, counts, static_cast<cudaStream_t>(stream)),
+            "person_counts");
+  return VIBO_OK;
+}
+
 int vibo_encode_backward(const vibo_desc* desc, const float* response, const uint8_t* mask,
                          const float* table, const float* ability_mu,
                          const float* precision_sum, const float* g_ability_mu,

@@ -443,6 +443,32 @@ __global__ void bernoulli_ll_kernel(int64_t n, const float* __restrict__ resp,
 }
 
 // ---------------------------------------------------------------------------
+// (n1, n_observed) per person: fallback of stream_counts for unaligned rows / I > 2048
+// (one warp per row, fixed summation order)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) person_counts_kernel(int64_t P, int I, const float* __restrict__ resp,
+                                                            const uint8_t* __restrict__ mask,
+                                                            float* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < P; row += nwarps) {
+    int n1 = 0, no = 0;
+    for (int j = lane; j < I; j += 32) {
+      const bool o = mask[row * I + j] != 0;
+      no += o ? 1 : 0;
+      n1 += (o && resp[row * I + j] > 0.5f) ? 1 : 0;
+    }
+    n1 = __reduce_add_sync(0xffffffffu, n1);
+    no = __reduce_add_sync(0xffffffffu, no);
+    if (lane == 0) {
+      counts[row * 2] = (float)n1;
+      counts[row * 2 + 1] = (float)no;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
 static unsigned long long g_launches = 0;
@@ -621,6 +647,23 @@ cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* ma
       return cudaErrorInvalidValue;
   }
   return e;
+}
+
+cudaError_t launch_person_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, float* counts,
+                                 cudaStream_t st) {
+  cudaError_t e = stream_counts(d, resp, mask, counts, st);
+  if (e != cudaErrorNotSupported) {
+    if (e == cudaSuccess) note_launch();
+    return e;
+  }
+  (void)cudaGetLastError();
+  int64_t blocks = (d.num_person + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  person_counts_kernel<<<(int)blocks, 256, 0, st>>>(d.num_person, d.num_item, resp, mask, counts);
+  note_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const vibo_desc& d, const float* ability, const float* item_feat,

@@ -38,6 +38,10 @@ cudaError_t launch_bernoulli_ll(const vibo_desc& d, const float* resp, const uin
 // covered; the launchers above then fall back to the legacy kernels.
 cudaError_t stream_encode(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table,
                           float* mu, float* lv, float* S, int* grid_out, cudaStream_t st);
+cudaError_t stream_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, float* counts,
+                          cudaStream_t st);
+cudaError_t launch_person_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, float* counts,
+                                 cudaStream_t st);
 cudaError_t stream_link(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* ability,
                         const float* item_feat, double* part_ll, float* g_ability, float* part_g, bool grad,
                         int* grid_out, cudaStream_t st);

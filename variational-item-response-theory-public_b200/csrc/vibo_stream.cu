@@ -127,11 +127,11 @@ cudaError_t run_encode(const vibo_desc& d, const StreamPlan& pl, const StreamPar
   if (d.conditional) {
     auto k = encode_stream_kernel<D, M, NR, true>;
     if ((e = set_smem(k, pl.smem)) != cudaSuccess) return e;
-    k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, d.missing_policy, table, mu, lv, S);
+    k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, d.missing_policy, table, mu, lv, S, nullptr);
   } else {
     auto k = encode_stream_kernel<D, M, 8, false>;
     if ((e = set_smem(k, pl.smem)) != cudaSuccess) return e;
-    k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, d.missing_policy, table, mu, lv, S);
+    k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, d.missing_policy, table, mu, lv, S, nullptr);
   }
   return cudaGetLastError();
 }
@@ -295,6 +295,34 @@ cudaError_t stream_encode(const vibo_desc& d, const float* resp, const uint8_t* 
   VIBO_STREAM_SWITCH_D(d.ability_dim,
                        VIBO_STREAM_SWITCH_M(pl.M, e = (run_encode<kD, kM>(d, pl, p, table, mu, lv, S, st))));
   if (grid_out) *grid_out = pl.grid;
+  return e;
+}
+
+// (n1, n_observed) per person, (P, 2) floats: the sufficient statistics of an unconditional encoder.
+cudaError_t stream_counts(const vibo_desc& d0, const float* resp, const uint8_t* mask, float* counts,
+                          cudaStream_t st) {
+  if (!aligned16(resp) || !aligned16(mask)) return cudaErrorNotSupported;
+  vibo_desc d = d0;
+  d.conditional = 0;
+  d.ability_dim = 1;
+  const StreamPlan pl = stream_plan(d, 0, 0);
+  if (!pl.ok) return cudaErrorNotSupported;
+  const StreamParams p = make_params(d, pl, resp, mask, 0, nullptr);
+  cudaError_t e = cudaErrorInvalidValue;
+#define VIBO_COUNTS_CASE(M_)                                                                   \
+  case M_: {                                                                                   \
+    auto k = encode_stream_kernel<1, M_, 8, false>;                                            \
+    if ((e = set_smem(k, pl.smem)) != cudaSuccess) return e;                                   \
+    k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, d.missing_policy, nullptr, nullptr, nullptr, nullptr, counts); \
+    e = cudaGetLastError();                                                                    \
+  } break;
+  switch (pl.M) {
+    VIBO_COUNTS_CASE(1)
+    VIBO_COUNTS_CASE(2)
+    VIBO_COUNTS_CASE(4)
+    default: break;
+  }
+#undef VIBO_COUNTS_CASE
   return e;
 }
 

@@ -195,7 +195,9 @@ template <int D, int M, int NR, bool COND>
 __global__ void __launch_bounds__(512) encode_stream_kernel(const __grid_constant__ StreamParams p,
                                                             int missing_policy, const float* __restrict__ table,
                                                             float* __restrict__ out_mu, float* __restrict__ out_lv,
-                                                            float* __restrict__ out_S) {
+                                                            float* __restrict__ out_S,
+                                                            float* __restrict__ out_counts) {
+  // out_counts (unconditional only): write (n1, n_observed) per person instead of the posterior
   extern __shared__ __align__(128) unsigned char smem[];
   const StreamCtx cx = stream_setup(p, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
@@ -343,6 +345,13 @@ __global__ void __launch_bounds__(512) encode_stream_kernel(const __grid_constan
         for (int w = 0; w < NW; ++w) {
           n1 += red[((size_t)r * NW + w) * Q];
           nm += red[((size_t)r * NW + w) * Q + 1];
+        }
+        if (out_counts != nullptr) {
+          if (d == 0) {
+            out_counts[(c * R + r) * 2] = n1;
+            out_counts[(c * R + r) * 2 + 1] = (float)I - nm;
+          }
+          continue;
         }
         const float nz = (float)I - nm - n1;
         const float mu0 = table[d], mu1 = table[2 * D + d];

@@ -279,3 +279,15 @@ def flow_person_backward(ability_mu, ability_logvar, eps, uhat, w, b, g_ability_
                                        _stream(dev))
     _lib.check(rc, "vibo_flow_person_backward")
     return g_mu, g_lv, g_uhat, g_w, g_b
+
+
+def person_counts(response, mask):
+    """vibo_person_counts -> (P, 2) float32: (observed ones, observed cells) per person."""
+    _check_rows(response, mask)
+    P, I = response.shape
+    desc = make_desc(P, I, 1, 2, False)
+    counts = torch.empty(P, 2, dtype=torch.float32, device=response.device)
+    rc = _lib.load().vibo_person_counts(C.byref(desc), _ptr(response), _ptr(mask), _ptr(counts),
+                                        _stream(response.device))
+    _lib.check(rc, "vibo_person_counts")
+    return counts

@@ -98,6 +98,12 @@ class AbilityInferenceNetwork(nn.Module):
         masked mean over items, mlp2.  resp (P, I) f32, msk (P, I) u8."""
         rows, It = self._cell_rows(item_feat)
         hid = F.elu(self.mlp1(rows)).reshape(2, It, self.hidden_dim)
+        if It == 1 and resp.is_cuda:
+            counts = VF.K.person_counts(resp, msk)   # one streaming pass: (ones, observed) per person
+            n1, n_obs = counts[:, 0:1], counts[:, 1:2]
+            hid_mean = ((n_obs - n1) * hid[0] + n1 * hid[1]) / n_obs
+            mu, logvar = torch.chunk(self.mlp2(hid_mean), 2, dim=1)
+            return mu, logvar
         obs = msk != 0
         one = (resp > 0.5) & obs
         n_obs = obs.sum(1, keepdim=True).to(hid.dtype)
