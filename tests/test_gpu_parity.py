@@ -6,6 +6,8 @@ Tolerance: the north-star bar is 1e-4 relative on the ELBO and on every
 parameter gradient (BASELINE.json).  Value-level checks against the fp64
 closed-form oracle use tighter bounds where fp32 arithmetic allows.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -362,3 +364,47 @@ def test_person_counts_kernel(vb, P, I, missing, offset):
     obs = m != 0
     ref = torch.stack([((r > 0.5) & obs).sum(1), obs.sum(1)], 1).float()
     assert torch.equal(counts, ref)
+
+
+def _fuzz_configs(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        irt = int(rng.integers(1, 4))
+        D = int(rng.integers(1, 9))
+        cond = bool(rng.integers(0, 2))
+        I = int(rng.choice([4, 7, 16, 17, 31, 32, 33, 64, 95, 100, 127, 128, 129, 255, 256, 257, 500, 512, 513,
+                            640, 1000, 1023, 1024, 1025, 1536, 2047, 2048]))
+        P = int(rng.choice([1, 2, 7, 8, 9, 15, 16, 17, 31, 33, 63, 64, 65, 100, 257, 1000, 2049]))
+        missing = float(rng.choice([0.0, 0.0, 0.05, 0.3, 0.9]))
+        policy = int(rng.integers(0, 2))
+        form = int(rng.integers(0, 2))
+        out.append((P, I, D, irt, cond, missing, policy, form))
+    return out
+
+
+@pytest.mark.parametrize("P,I,D,irt,cond,missing,policy,form",
+                         _fuzz_configs(int(os.environ.get("VIBO_FUZZ_N", "48")),
+                                       int(os.environ.get("VIBO_FUZZ_SEED", "20261017"))))
+def test_paths_agree_on_random_shapes(vb, monkeypatch, P, I, D, irt, cond, missing, policy, form):
+    """Differential fuzz over shapes that straddle every tile / slab / stage boundary: the
+    default dispatch (single-pass, tensor-core or slab-stream kernels) against the legacy
+    row-slab kernels on identical inputs."""
+    if I > 1024 and D > 4:
+        pytest.skip("legacy kernels: I <= 1024 for D > 4")
+    resp, mask, table, item, eps = _synth(P, I, D, irt, cond, missing, seed=P * 31 + I * 7 + D)
+    kw = dict(irt_model=irt, conditional=cond, missing_policy=policy, elbo_form=form, beta=0.6)
+    a = _run_fused(vb, resp, mask, table, item, eps, **kw)
+    monkeypatch.setenv("VIBO_DISABLE_FUSED", "1")
+    monkeypatch.setenv("VIBO_DISABLE_MMA", "1")
+    monkeypatch.setenv("VIBO_DISABLE_STREAM", "1")
+    b = _run_fused(vb, resp, mask, table, item, eps, **kw)
+    fin = np.isfinite(b["ability_mu"]).all(axis=1)      # all-missing rows under drop-missing are NaN in both
+    assert np.array_equal(np.isfinite(a["ability_mu"]).all(axis=1), fin)
+    if fin.all():
+        for k in (0, 1):
+            assert abs(a["scalars"][k] - b["scalars"][k]) <= TOL * max(abs(b["scalars"][k]), 1.0), k
+        assert rel_l2(a["g_item"], b["g_item"]) < TOL
+        assert rel_l2(a["g_table"], b["g_table"]) < TOL
+    for k in ("ability_mu", "ability_logvar", "ability"):
+        assert max_rel(a[k][fin], b[k][fin]) < TOL, k
