@@ -385,7 +385,11 @@ def _fuzz_configs(n, seed):
 
 @pytest.mark.parametrize("P,I,D,irt,cond,missing,policy,form",
                          _fuzz_configs(int(os.environ.get("VIBO_FUZZ_N", "48")),
-                                       int(os.environ.get("VIBO_FUZZ_SEED", "20261017"))))
+                                       int(os.environ.get("VIBO_FUZZ_SEED", "20261017")))
+                         # rows with no observed cell at all (a 400-config fuzz run found the tensor-core
+                         # encode returning a rounding residue instead of NaN under drop-missing)
+                         + [(65, 16, 2, 3, True, 0.9, 1, 0), (65, 16, 2, 3, True, 0.9, 0, 0),
+                            (40, 32, 5, 2, True, 0.95, 1, 1)])
 def test_paths_agree_on_random_shapes(vb, monkeypatch, P, I, D, irt, cond, missing, policy, form):
     """Differential fuzz over shapes that straddle every tile / slab / stage boundary: the
     default dispatch (single-pass, tensor-core or slab-stream kernels) against the legacy

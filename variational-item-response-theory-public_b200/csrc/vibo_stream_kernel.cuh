@@ -1084,6 +1084,13 @@ __global__ void __launch_bounds__(kMmaWarps * 32) encode_mma_kernel(const __grid
         }
         sv = (base[d] - cS) + sv + cm * prior_tau;
         nv = (base[D + d] - cN) + nv;
+        if (has_missing && cm >= (float)I) {
+          // no observed cell: base - correction is a rounding residue, not zero.  Exact values
+          // instead: prior experts only, or (--drop-missing) an empty product -> 0 / 0 = NaN,
+          // as in the reference (models.py:614-621).
+          sv = cm * prior_tau;
+          nv = 0.0f;
+        }
         const int64_t row = c * R + r0 + r;
         out_mu[row * D + d] = nv / sv;
         out_lv[row * D + d] = logf(1.0f / sv);
