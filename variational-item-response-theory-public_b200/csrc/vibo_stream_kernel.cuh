@@ -924,9 +924,9 @@ __global__ void __launch_bounds__(kMmaWarps * 32) encode_mma_kernel(const __grid
   __syncthreads();
   // base sums over all items, fixed order (thread k < 2D)
   if ((int)threadIdx.x < 2 * D) {
-    float acc = 0.0f;
-    for (int j = 0; j < I; ++j) acc += tab[j * 2 * D + threadIdx.x];
-    base[threadIdx.x] = acc;
+    double acc = 0.0;   // the missing-cell corrections are subtracted from this sum: keep it tight
+    for (int j = 0; j < I; ++j) acc += (double)tab[j * 2 * D + threadIdx.x];
+    base[threadIdx.x] = (float)acc;
   }
   const float prior_tau = (missing_policy == VIBO_MISSING_PRIOR) ? 1.0f / (1.0f + kPoeEps) : 0.0f;
   __syncthreads();
