@@ -298,3 +298,49 @@ def person_counts(response, mask):
     n1 = one.sum(1)
     nobs = obs.sum(1)
     return nobs - n1, n1, response.shape[1] - nobs
+
+
+# ---------------------------------------------------------------------------
+# Planar flows on the abilities, fused per person (spec of vibo_flow_person_forward /
+# vibo_flow_person_backward; reference src/torch_core/flows.py:21-41, :58-66 and the flow form
+# of the ELBO, src/torch_core/models.py:406-424).  uhat is the invertibility-corrected u
+# (flows.py:26-29), formed by the caller.
+# ---------------------------------------------------------------------------
+def flow_person(ability_mu, ability_logvar, eps, uhat, w, b, g_ability_k=None, g_term=0.0):
+    """Forward: theta_0 = mu + eps exp(lv / 2); K planar steps; term = sum_i [log N(theta_K; 0, 1)
+    - log N(theta_0; mu, exp lv) + sum_k ldj_k].  With ``g_ability_k`` (d loss / d theta_K) and
+    ``g_term`` (d loss / d term) also the closed-form backward."""
+    mu, lv, eps = (np.asarray(a, dtype=np.float64) for a in (ability_mu, ability_logvar, eps))
+    uhat, w, b = (np.asarray(a, dtype=np.float64) for a in (uhat, w, b))
+    K = uhat.shape[0]
+    sd = np.exp(0.5 * lv)
+    z = mu + eps * sd
+    theta0 = z.copy()
+    zin, hs = [], []
+    wu = (w * uhat).sum(1)
+    ldj = np.zeros(mu.shape[0])
+    for k in range(K):
+        zin.append(z.copy())
+        h = np.tanh(z @ w[k] + b[k])
+        hs.append(h)
+        z = z + h[:, None] * uhat[k][None, :]
+        ldj += np.log(np.abs(1.0 + (1.0 - h * h) * wu[k]) + 1e-8)
+    term = float((-0.5 * z ** 2 + 0.5 * eps ** 2 + 0.5 * lv).sum() + ldj.sum())
+    out = dict(ability_0=theta0, ability_k=z, term=term)
+    if g_ability_k is None:
+        return out
+    c = float(g_term)
+    G = np.asarray(g_ability_k, dtype=np.float64) - c * z
+    g_uhat, g_w, g_b = np.zeros_like(uhat), np.zeros_like(w), np.zeros_like(b)
+    for k in range(K - 1, -1, -1):
+        h = hs[k]
+        omh = 1.0 - h * h
+        q = 1.0 + omh * wu[k]
+        dl = c * np.where(q >= 0, 1.0, -1.0) / (np.abs(q) + 1e-8)        # d loss / d s_k
+        ga = (G @ uhat[k]) * omh + dl * (-2.0 * h * omh) * wu[k]          # d loss / d a_k
+        g_uhat[k] = (G * h[:, None]).sum(0) + (dl * omh).sum() * w[k]
+        g_w[k] = (ga[:, None] * zin[k]).sum(0) + (dl * omh).sum() * uhat[k]
+        g_b[k] = ga.sum()
+        G = G + ga[:, None] * w[k][None, :]
+    out.update(g_mu=G, g_logvar=0.5 * G * eps * sd + 0.5 * c, g_uhat=g_uhat, g_w=g_w, g_b=g_b)
+    return out

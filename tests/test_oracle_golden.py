@@ -119,3 +119,43 @@ def test_person_counts_equivalence():
     perm = rng.permutation(I)
     enc2 = KS.encode(resp[:, perm], mask[:, perm], table, D)
     assert np.allclose(enc2["ability_mu"], enc["ability_mu"])
+
+
+@pytest.mark.parametrize("D,K", [(1, 2), (3, 1), (4, 5)])
+def test_flow_person_spec_matches_reference_port(D, K):
+    """oracle/kernel_spec.flow_person (the closed form the CUDA flow kernels implement) against
+    the literal port's planar flows under float64 autograd."""
+    torch.manual_seed(D * 10 + K)
+    P = 37
+    p = {}
+    for k in range(K):
+        p[f"ability_norm_flows.flows.{k}.u"] = torch.randn(D, dtype=torch.float64, requires_grad=True)
+        p[f"ability_norm_flows.flows.{k}.w"] = torch.randn(D, dtype=torch.float64, requires_grad=True)
+        p[f"ability_norm_flows.flows.{k}.b"] = torch.ones(1, dtype=torch.float64, requires_grad=True)
+    mu = torch.randn(P, D, dtype=torch.float64, requires_grad=True)
+    lv = (0.3 * torch.randn(P, D, dtype=torch.float64) - 1.0).requires_grad_()
+    eps = torch.randn(P, D, dtype=torch.float64)
+    w_ll = torch.randn(P, D, dtype=torch.float64)
+    t0 = RP.reparameterize(mu, lv, eps)
+    tk, ldj = RP.planar_flows(p, "ability_norm_flows", K, t0)
+    term = RP.standard_normal_log_pdf(tk).sum() - (RP.normal_log_pdf(t0, mu, lv).sum() - ldj.sum())
+    loss = -((tk * w_ll).sum() + 0.7 * term)
+    loss.backward()
+    # uhat as the product forms it (flows.py:26-29), with autograd to map g_uhat back to (u, w)
+    us = [p[f"ability_norm_flows.flows.{k}.u"].detach().clone().requires_grad_() for k in range(K)]
+    ws = [p[f"ability_norm_flows.flows.{k}.w"].detach().clone().requires_grad_() for k in range(K)]
+    uhat = torch.stack([u + (torch.nn.functional.softplus((u * w).sum()) - 1.0 - (u * w).sum()) * w / (w * w).sum()
+                        for u, w in zip(us, ws)])
+    out = KS.flow_person(mu.detach().numpy(), lv.detach().numpy(), eps.numpy(), uhat.detach().numpy(),
+                         torch.stack(ws).detach().numpy(), np.ones(K), g_ability_k=-w_ll.numpy(), g_term=-0.7)
+    assert np.allclose(out["ability_k"], tk.detach().numpy(), rtol=1e-12, atol=1e-12)
+    assert abs(out["term"] - term.item()) < 1e-9 * max(1.0, abs(term.item()))
+    assert np.allclose(out["g_mu"], mu.grad.numpy(), rtol=1e-9, atol=1e-11)
+    assert np.allclose(out["g_logvar"], lv.grad.numpy(), rtol=1e-9, atol=1e-11)
+    (uhat * torch.from_numpy(out["g_uhat"])).sum().backward()
+    for k in range(K):
+        g_u = us[k].grad.numpy()
+        g_w = ws[k].grad.numpy() + out["g_w"][k]
+        assert np.allclose(g_u, p[f"ability_norm_flows.flows.{k}.u"].grad.numpy(), rtol=1e-8, atol=1e-10)
+        assert np.allclose(g_w, p[f"ability_norm_flows.flows.{k}.w"].grad.numpy(), rtol=1e-8, atol=1e-10)
+        assert abs(out["g_b"][k] - p[f"ability_norm_flows.flows.{k}.b"].grad.item()) < 1e-8 * max(1, abs(out["g_b"][k]))
