@@ -83,3 +83,33 @@ def test_masked_cells_do_not_matter(seed, I, D):
     resp2 = resp.copy(); resp2[mask == 0] = rng.choice([0.0, 1.0, -1.0, 7.0], size=int((mask == 0).sum()))
     b = KS.fused_elbo(resp2, mask, table, item, eps, irt_model=2)
     assert a["ll"] == b["ll"] and np.array_equal(a["g_item"], b["g_item"])
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.tuples(st.integers(1, 4), st.integers(1, 4), st.integers(0, 10 ** 6)))
+def test_flow_person_gradients_match_finite_differences(s):
+    """Closed-form backward of the fused planar-flow person kernels (oracle/kernel_spec.flow_person)
+    against central differences of its own forward, for the loss  w.theta_K + c * term."""
+    D, K, seed = s
+    rng = np.random.default_rng(seed)
+    P = 5
+    mu, lv, eps = rng.normal(size=(P, D)), 0.3 * rng.normal(size=(P, D)) - 1.0, rng.normal(size=(P, D))
+    uhat, w, b = 0.6 * rng.normal(size=(K, D)), 0.6 * rng.normal(size=(K, D)), rng.normal(size=K)
+    wll, c = rng.normal(size=(P, D)), 0.7
+
+    def loss(mu_, lv_, uhat_, w_, b_):
+        o = KS.flow_person(mu_, lv_, eps, uhat_, w_, b_)
+        return float((o["ability_k"] * wll).sum() + c * o["term"])
+
+    out = KS.flow_person(mu, lv, eps, uhat, w, b, g_ability_k=wll, g_term=c)
+    h = 1e-6
+    for name, arr, g in (("mu", mu, out["g_mu"]), ("lv", lv, out["g_logvar"]), ("uhat", uhat, out["g_uhat"]),
+                         ("w", w, out["g_w"]), ("b", b, out["g_b"])):
+        idx = tuple(rng.integers(0, n) for n in arr.shape)
+        args = dict(mu_=mu, lv_=lv, uhat_=uhat, w_=w, b_=b)
+        key = {"mu": "mu_", "lv": "lv_", "uhat": "uhat_", "w": "w_", "b": "b_"}[name]
+        up, dn = arr.copy(), arr.copy()
+        up[idx] += h
+        dn[idx] -= h
+        fd = (loss(**{**args, key: up}) - loss(**{**args, key: dn})) / (2 * h)
+        assert np.isclose(fd, g[idx], rtol=2e-5, atol=2e-6), (name, fd, g[idx])
