@@ -3,10 +3,15 @@
 // ability_dim up to 8, 3PL, any number of items (no alignment requirement on
 // I), missing data -- at streaming speed.
 //
-//   encode_stream_kernel      product-of-experts sums   (models.py:596-629, utils.py:105-113)
+//   encode_stream_kernel      product-of-experts sums   (models.py:596-629, utils.py:105-113);
+//                             unconditional: two counts per person (also vibo_person_counts)
 //   link_stream_kernel        link + Bernoulli log-lik  (models.py:729-766, utils.py:46-49)
 //                             + d/d ability, d/d item_feat
 //   encode_bwd_stream_kernel  per-(response value, item) sums of the expert-table gradient
+//   encode_mma_kernel         conditional product-of-experts sums on the tensor cores
+//                             (bf16 x 3 split, mma.sync m16n8k16)
+//   encode_bwd_mma_kernel     conditional expert-table gradient sums on the tensor cores
+//                             (tf32 x 2 split, mma.sync m16n8k8)
 //
 // Shared skeleton.  A persistent CTA streams chunks of R rows (response f32 +
 // mask u8 + the per-person arrays the pass needs) through a ring of NS
