@@ -344,3 +344,25 @@ def flow_person(ability_mu, ability_logvar, eps, uhat, w, b, g_ability_k=None, g
         G = G + ga[:, None] * w[k][None, :]
     out.update(g_mu=G, g_logvar=0.5 * G * eps * sd + 0.5 * c, g_uhat=g_uhat, g_w=g_w, g_b=g_b)
     return out
+
+
+# ---------------------------------------------------------------------------
+# --ability-merge mean (reference src/torch_core/models.py:584-594, :631-650) with the table
+# collapse: the per-cell hidden vector takes 2 (unconditional) or 2 I (conditional) distinct
+# values, so the per-person masked mean is  (indicator or counts) x hidden table / n_observed.
+# ---------------------------------------------------------------------------
+def mean_merge_hidden(response, mask, hidden_table):
+    """hidden_table (2, It, H) -> (P, H) masked mean of the selected hidden vectors.
+    Rows without any observed cell give NaN (0 / 0), like the reference's mean of an empty set."""
+    x = np.asarray(response, dtype=np.float64)
+    o = np.asarray(mask) != 0
+    T = np.asarray(hidden_table, dtype=np.float64)
+    one = (x > 0.5) & o
+    zero = o & ~one
+    if T.shape[1] == 1:
+        n0, n1, _ = person_counts(response, mask)
+        tot = n0[:, None] * T[0, 0][None, :] + n1[:, None] * T[1, 0][None, :]
+    else:
+        tot = one.astype(np.float64) @ T[1] + zero.astype(np.float64) @ T[0]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return tot / o.sum(1, keepdims=True)

@@ -159,3 +159,29 @@ def test_flow_person_spec_matches_reference_port(D, K):
         assert np.allclose(g_u, p[f"ability_norm_flows.flows.{k}.u"].grad.numpy(), rtol=1e-8, atol=1e-10)
         assert np.allclose(g_w, p[f"ability_norm_flows.flows.{k}.w"].grad.numpy(), rtol=1e-8, atol=1e-10)
         assert abs(out["g_b"][k] - p[f"ability_norm_flows.flows.{k}.b"].grad.item()) < 1e-8 * max(1, abs(out["g_b"][k]))
+
+
+@pytest.mark.parametrize("name", [n for n in CASE_NAMES if "_mean_" in n])
+def test_mean_merge_spec_matches_reference(name):
+    """Table-collapsed masked mean (oracle/kernel_spec.mean_merge_hidden) + mlp2 reproduce the
+    live reference's ability posterior for --ability-merge mean."""
+    cfg, rec, params, _ = load_case(name)
+    P64 = {k: v.double() for k, v in params.items()}
+    I, cond = cfg["I"], cfg["conditional"]
+    F = torch.nn.functional
+    if cond:
+        item_feat = torch.from_numpy(rec["item_feat"]).double()
+        r = torch.zeros(2, I, 1, dtype=torch.float64)
+        r[1] = 1
+        rows = torch.cat([r, item_feat.unsqueeze(0).expand(2, I, -1)], 2).reshape(2 * I, -1)
+    else:
+        rows = torch.tensor([[0.0], [1.0]], dtype=torch.float64)
+    h = F.elu(F.linear(rows, P64["ability_encoder.mlp1.0.weight"], P64["ability_encoder.mlp1.0.bias"]))
+    h = F.elu(F.linear(h, P64["ability_encoder.mlp1.2.weight"], P64["ability_encoder.mlp1.2.bias"]))
+    table = h.reshape(2, I if cond else 1, -1).numpy()
+    hid_mean = torch.from_numpy(KS.mean_merge_hidden(rec["response"], rec["mask"], table))
+    o = F.elu(F.linear(hid_mean, P64["ability_encoder.mlp2.0.weight"], P64["ability_encoder.mlp2.0.bias"]))
+    o = F.linear(o, P64["ability_encoder.mlp2.2.weight"], P64["ability_encoder.mlp2.2.bias"])
+    mu, lv = torch.chunk(o, 2, dim=1)
+    assert max_rel(mu.numpy(), rec["ability_mu"]) < 1e-5
+    assert max_rel(lv.numpy(), rec["ability_logvar"]) < 1e-5
