@@ -165,38 +165,100 @@ def ncu_traffic(workload, mode):
 # --------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # --------------------------------------------------------------------------
+REF_ROOT = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_sample_persons(P, I, steps, warmup, batch, mode="eval", miss=0.0):
+    """Per-step sample of the workload for the CPU arm: sized so that the whole
+    --steps K --warmup W run ends within ~2 minutes at the rate the reference
+    reaches on a 16-core host (~8 M cells/s forward, ~2 M cells/s training step,
+    ~0.2 M cells/s with missing data: per-person python loop, models.py:608-625),
+    capped at 4 M cells per step."""
+    rate = 0.2e6 if miss > 0 else (2e6 if mode == "train" else 8e6)
+    cells = min(4_000_000, int(120 * rate / max(1, steps + warmup)))
+    return max(batch, min(P, (cells // I) // batch * batch))
+
+
 def run_reference_cpu(workload, steps, warmup, mode, sample_persons=None, batch=256):
-    """Times the reference's own CPU implementation of the step -- per-cell
-    encoder MLP over (B*I, 1) rows, PoE, torch.mm link, Bernoulli.log_prob,
-    autograd backward, Adam: oracle/reference_port.py restates
-    src/torch_core/models.py + vibo.py:243-268 op for op (/root/reference is
-    not present on the GPU box, so the port stands in: kind "port")."""
+    """Times the reference's own CPU implementation of the step on the host
+    cores.  kind "reference": the UNMODIFIED reference modules
+    (src/torch_core/models.py VIBO_*PL.forward + .elbo + backward + Adam, the
+    body of vibo.py:243-268), imported from baseline/_ref (a git-ignored copy of
+    the reference's pure-Python sources made by __graft_entry__.build(); it
+    travels to the GPU box with the snapshot).  kind "port": if that copy is
+    absent, oracle/reference_port.py, which restates the same op sequence."""
     import torch
-    from oracle import reference_port as RP
     irt, P, I, D, cond, miss, flows = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     if sample_persons is None:
-        # sized for ~2 s per step at the ~2 Mcells/s the reference reaches (BASELINE.md)
-        sample_persons = max(batch, min(P, (4_000_000 // I) // batch * batch))
+        sample_persons = reference_sample_persons(P, I, steps, warmup, batch, mode, miss)
     resp, mask = synth_rows(sample_persons, I, D, irt, miss, "cpu")
     mask_l = mask.long()
     torch.manual_seed(42)
-    params = RP.init_params(irt, D, I, conditional=cond, n_flows=flows)
-    state = {}
-    F = RP.item_feat_width(irt, D)
-    kw = dict(irt_model=irt, ability_dim=D, conditional=cond, n_flows=flows,
-              use_kl_divergence=(flows == 0))
+    kind = "port"
+    model = None
+    if os.path.exists(os.path.join(REF_ROOT, "src", "torch_core", "models.py")):
+        try:
+            if REF_ROOT not in sys.path:
+                sys.path.insert(0, REF_ROOT)
+            from src.torch_core import models as ref_models  # the reference, unmodified
+            # missing cells hold -1: the reference relies on python -O-less validation being off
+            torch.distributions.Distribution.set_default_validate_args(False)
+            cls = {1: ref_models.VIBO_1PL, 2: ref_models.VIBO_2PL, 3: ref_models.VIBO_3PL}[irt]
+            model = cls(D, I, hidden_dim=64, ability_merge="product", conditional_posterior=cond,
+                        generative_model="irt", response_dist="bernoulli", n_norm_flows=flows)
+            opt = torch.optim.Adam(model.parameters(), lr=5e-3)  # vibo.py:221
+            kind = "reference"
+        except Exception as ex:  # fall back to the port, say why
+            print(f"[bench] unmodified reference unavailable ({ex!r}); timing the oracle port", file=sys.stderr)
+            model = None
 
-    def one_step():
-        for a in range(0, sample_persons, batch):
-            r, m = resp[a:a + batch], mask_l[a:a + batch]
-            e_i = torch.randn(I, F)
-            e_a = torch.randn(r.shape[0], D)
-            if mode == "train":
-                RP.adam_train_step(params, state, r, m, e_i, e_a, **kw)
-            else:
-                RP.loss_and_grads(params, r, m, e_i, e_a, want_grads=False, **kw)
+    if model is not None:
+        def one_step():
+            for a in range(0, sample_persons, batch):
+                r, m = resp[a:a + batch], mask_l[a:a + batch]
+                if mode == "train":
+                    model.train()
+                    opt.zero_grad()
+                    out = model(r, m)
+                    if flows > 0:
+                        (r_, m_, mu, a_k, ab, a_mu, a_lv, a_ldj, i_k, it, i_mu, i_lv, i_ldj) = out
+                        loss = model.elbo(r_, m_, mu, ab, a_mu, a_lv, it, i_mu, i_lv, annealing_factor=1.0,
+                                          use_kl_divergence=False, ability_k=a_k, item_feat_k=i_k,
+                                          ability_logabsdetjac=a_ldj, item_logabsdetjac=i_ldj)
+                    else:
+                        loss = model.elbo(*out, annealing_factor=1.0, use_kl_divergence=True)
+                    loss.backward()
+                    opt.step()
+                else:
+                    model.eval()
+                    with torch.no_grad():
+                        out = model(r, m)
+                        if flows > 0:
+                            (r_, m_, mu, a_k, ab, a_mu, a_lv, a_ldj, i_k, it, i_mu, i_lv, i_ldj) = out
+                            model.elbo(r_, m_, mu, ab, a_mu, a_lv, it, i_mu, i_lv, use_kl_divergence=False,
+                                       ability_k=a_k, item_feat_k=i_k, ability_logabsdetjac=a_ldj,
+                                       item_logabsdetjac=i_ldj)
+                        else:
+                            model.elbo(*out, use_kl_divergence=True)
+    else:
+        from oracle import reference_port as RP
+        params = RP.init_params(irt, D, I, conditional=cond, n_flows=flows)
+        state = {}
+        F = RP.item_feat_width(irt, D)
+        kw = dict(irt_model=irt, ability_dim=D, conditional=cond, n_flows=flows,
+                  use_kl_divergence=(flows == 0))
+
+        def one_step():
+            for a in range(0, sample_persons, batch):
+                r, m = resp[a:a + batch], mask_l[a:a + batch]
+                e_i = torch.randn(I, F)
+                e_a = torch.randn(r.shape[0], D)
+                if mode == "train":
+                    RP.adam_train_step(params, state, r, m, e_i, e_a, **kw)
+                else:
+                    RP.loss_and_grads(params, r, m, e_i, e_a, want_grads=False, **kw)
 
     for _ in range(warmup):
         one_step()
@@ -205,9 +267,10 @@ def run_reference_cpu(workload, steps, warmup, mode, sample_persons=None, batch=
         one_step()
     dt = time.perf_counter() - t0
     cells = sample_persons * I * steps
-    return {"value": cells / dt, "ms_per_step": dt / steps * 1e3, "cores": cores,
+    return {"value": cells / dt, "ms_per_step": dt / steps * 1e3, "cores": cores, "kind": kind,
             "sample": f"{sample_persons} persons x {I} items in minibatches of {batch} "
-                      f"({mode} step, fp32, {torch.get_num_threads()} torch threads)"}
+                      f"({mode} step, fp32, {torch.get_num_threads()} torch threads, "
+                      f"{'unmodified reference modules' if kind == 'reference' else 'oracle port'})"}
 
 
 def main():
@@ -220,9 +283,12 @@ def main():
     ap.add_argument("--mode", default="eval", choices=["train", "eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra-workloads", default="c2,c3,c5",
+    ap.add_argument("--extra-workloads", default="c1,c2,c3,c5",
                     help="other BASELINE.json configs timed after the headline at N=1 (comma list, '' = none)")
     ap.add_argument("--cuda-graph", type=int, default=1, help="capture the step in a CUDA graph (1/0)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "dist"],
+                    help="per-step exchange at N > 1: peer-memory kernel inside the graph (auto/peer) or "
+                         "torch.distributed NCCL between two graphs (dist)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -235,22 +301,23 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 10))
-        r = run_reference_cpu(args.workload, steps, max(1, min(args.warmup, 2)), args.mode)
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        r = run_reference_cpu(args.workload, steps, warm, args.mode)
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "cells/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": describe(args.workload), "mode": args.mode,
                            "note": "CPU; each step is a bounded sample of the workload"},
                 "cpu_baseline": {"value": r["value"], "unit": "cells/s", "cores": r["cores"],
-                                 "kind": "port", "sample": r["sample"]},
+                                 "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "cells/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     # --------------------------------------------------------------- native arm
+    import ctypes
     import torch
     import torch.distributed as dist
     import vibo_b200
@@ -261,107 +328,141 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = vibo_b200._lib.load()
-
-    resp, mask = synth_rows(P, I, D, irt, miss, dev, seed=42 + rank)
-    torch.manual_seed(42)
-    cls = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[irt]
-    model = cls(D, I, hidden_dim=64, ability_merge="product", conditional_posterior=cond,
-                n_norm_flows=flows).to(dev)
-    trainer = vdist.ShardedElboTrainer(model, lr=5e-3, world_size=world, rank=rank,
-                                       person_offset=rank * P, use_kl_divergence=(flows == 0),
-                                       cuda_graph=bool(args.cuda_graph))
-
-    import ctypes
     peak, peak_src = measured_peak()
 
-    def run(mode, i, eager=False, rows=None):
-        r, m = rows if rows is not None else (resp, mask)
-        if mode == "train":
-            return trainer.train_step(r, m, step_index=i, force_eager=eager)
-        return trainer.eval_step(r, m, step_index=i, force_eager=eager)
+    def make(workload_name, world_=1, rank_=0, offset=0, seed_rows=42):
+        irt_, P_, I_, D_, cond_, miss_, flows_ = WORKLOADS[workload_name]
+        r_, m_ = synth_rows(P_, I_, D_, irt_, miss_, dev, seed=seed_rows)
+        torch.manual_seed(42)
+        cls = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[irt_]
+        model_ = cls(D_, I_, hidden_dim=64, ability_merge="product", conditional_posterior=cond_,
+                     n_norm_flows=flows_).to(dev)
+        tr_ = vdist.ShardedElboTrainer(model_, lr=5e-3, world_size=world_, rank=rank_, person_offset=offset,
+                                       use_kl_divergence=(flows_ == 0), cuda_graph=bool(args.cuda_graph),
+                                       allreduce=args.allreduce)
+        return r_, m_, model_, tr_
 
-    def time_mode(mode, sampler=None):
-        """W warm-up steps, then K timed steps bracketed by barrier + synchronize;
-        device time by CUDA events, max over ranks."""
-        for i in range(max(args.warmup, 3)):
-            run(mode, i)
+    def step_fn(tr, mode):
+        return tr.train_step if mode == "train" else tr.eval_step
+
+    def time_steps(tr, mode, rows, steps, warmup, sampler=None, collective=True):
+        """`warmup` untimed steps, then `steps` timed steps bracketed by barrier +
+        synchronize; device time by CUDA events on the launching stream, max over ranks."""
+        fn = step_fn(tr, mode)
+        for _ in range(max(warmup, 3)):
+            fn(*rows)
         torch.cuda.synchronize()
         if sampler is not None:
             sampler.start()
             time.sleep(0.3)
-        if world > 1:
+        if world > 1 and collective:
             dist.barrier()
         torch.cuda.synchronize()
-        replays0 = trainer.graph_replays
-        launches0 = lib.vibo_launch_count()
+        replays0, launches0 = tr.graph_replays, lib.vibo_launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         ev0.record()
         out = None
-        for i in range(args.steps):
-            out = run(mode, args.warmup + i)
+        for _ in range(steps):
+            out = fn(*rows)
         ev1.record()
         torch.cuda.synchronize()
         t1 = time.time()
-        if world > 1:
+        if world > 1 and collective:
             dist.barrier()
         launches = int(lib.vibo_launch_count() - launches0)
-        graphed = trainer.graph_replays > replays0
+        graphed = tr.graph_replays > replays0
         if graphed:
-            launches = trainer.kernels_per_step * args.steps
+            launches = tr.kernels_per_step * steps
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        total_ms = float(ms.item())
         clocks = sampler.stop(t0, t1) if sampler is not None else None
-        # device time of the dominant kernel alone: CUDA events recorded around
-        # its launch on the launching stream (vibo_profile_*), on an un-graphed
-        # pass of the same step (a graph replay cannot carry the brackets)
+        return {"total_ms": float(ms.item()), "ms_per_step": float(ms.item()) / steps, "loss": float(out.item()),
+                "gpu_launches": launches, "cuda_graph": graphed, "clocks": clocks}
+
+    def kernel_roofline(tr, mode, rows, cells, workload_name):
+        """Device time of the dominant kernel alone: CUDA events recorded around its launch on the
+        launching stream (vibo_profile_*), on un-graphed passes of the same step."""
         n_l, tot = ctypes.c_int(0), ctypes.c_double(0.0)
+        fn = step_fn(tr, mode)
         lib.vibo_profile_begin()
-        for i in range(5):
-            run(mode, 1000 + i, eager=True)
+        for _ in range(5):
+            fn(*rows, force_eager=True)
         torch.cuda.synchronize()
         lib.vibo_profile_end(ctypes.byref(n_l), ctypes.byref(tot))
-        roofline = None
-        if n_l.value > 0:
-            k_ms = tot.value / n_l.value
-            achieved = P * I * BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": ncu_traffic(args.workload, mode),
-                        "kernel": ("fused2_kernel<GRAD=%s>" % ("true" if mode == "train" else "false"))
-                        if trainer.uses_fused else "general kernels",
-                        "kernel_ms": k_ms, "algorithmic_bytes_per_cell": BYTES_PER_CELL,
-                        "peak_source": peak_src}
-        return {"value": P * I * world * args.steps / (total_ms * 1e-3), "unit": "cells/s",
-                "ms_per_step": total_ms / args.steps, "evals_per_sec": args.steps / (total_ms * 1e-3),
-                "loss": float(out.item()), "gpu_launches": launches, "cuda_graph": graphed,
-                "roofline": roofline, "clocks": clocks}
+        if n_l.value <= 0:
+            return None
+        k_ms = tot.value / n_l.value
+        achieved = cells * BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(workload_name, mode),
+                "kernel": ("fused2_kernel<GRAD=%s>" % ("true" if mode == "train" else "false"))
+                if tr.uses_fused else "general kernels",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_cell": BYTES_PER_CELL, "peak_source": peak_src}
+
+    resp, mask, model, trainer = make(args.workload, world, rank, rank * P, seed_rows=42 + rank)
+    ar_kind = trainer.allreduce_kind
+
+    def time_mode(mode, sampler=None):
+        res = time_steps(trainer, mode, (resp, mask), args.steps, args.warmup, sampler)
+        res["value"] = P * I * world * args.steps / (res["total_ms"] * 1e-3)
+        res["unit"] = "cells/s"
+        res["evals_per_sec"] = args.steps / (res["total_ms"] * 1e-3)
+        res["roofline"] = kernel_roofline(trainer, mode, (resp, mask), P * I, args.workload)
+        res.pop("total_ms")
+        return res
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     main_res = time_mode(args.mode, sampler)
     other_mode = "train" if args.mode == "eval" else "eval"
     other_res = time_mode(other_mode)
-    total_ms = main_res["ms_per_step"] * args.steps
     value = main_res["value"]
 
+    # C4 AS STATED (BASELINE.json configs[3]): 1,000,000 x 1,000 persons split over the N GPUs
+    # (strong scaling), both modes, beside the same rank's un-sharded 1 M-row step (no exchange).
+    strong = None
+    if world > 1 and args.workload == "c4":
+        a0, a1 = vdist.shard_bounds(P, rank, world)
+        n_loc = a1 - a0
+        rs, ms_ = resp[:n_loc].contiguous(), mask[:n_loc].contiguous()
+        torch.manual_seed(42)
+        cls = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[irt]
+        strong = {"workload": f"{describe('c4')} split over {world} GPUs ({n_loc} rows per GPU)"}
+        for mode in ("train", "eval"):
+            m_s = cls(D, I, hidden_dim=64, ability_merge="product").to(dev)
+            tr_s = vdist.ShardedElboTrainer(m_s, lr=5e-3, world_size=world, rank=rank, person_offset=a0,
+                                            cuda_graph=bool(args.cuda_graph), allreduce=args.allreduce)
+            r_s = time_steps(tr_s, mode, (rs, ms_), args.steps, args.warmup)
+            m_1 = cls(D, I, hidden_dim=64, ability_merge="product").to(dev)
+            tr_1 = vdist.ShardedElboTrainer(m_1, lr=5e-3, cuda_graph=bool(args.cuda_graph))
+            r_1 = time_steps(tr_1, mode, (resp, mask), max(5, args.steps // 4), 3, collective=False)
+            strong[mode] = {"ms_per_step": r_s["ms_per_step"], "cells_per_s": P * I / (r_s["ms_per_step"] * 1e-3),
+                            "one_gpu_ms_per_step": r_1["ms_per_step"],
+                            "efficiency_vs_one_gpu": r_1["ms_per_step"] / (world * r_s["ms_per_step"]),
+                            "allreduce": tr_s.allreduce_kind, "cuda_graph": r_s["cuda_graph"]}
+            tr_s.close()
+            del m_s, tr_s, m_1, tr_1
+        del rs, ms_
+
     # end-to-end through the public API with HOST (pinned) rows: H2D of the
-    # step's rows and D2H of the loss inside the timed region.
+    # step's rows and D2H of the loss inside the timed region; the full workload.
     e2e = None
     if not args.no_e2e and flows == 0:
-        Pe = min(P, 262144) if args.workload == "c4" and os.environ.get("VIBO_E2E_FULL") != "1" else P
+        Pe = min(P, int(os.environ.get("VIBO_E2E_ROWS", P)))
         resp_h = resp[:Pe].cpu().pin_memory()
         mask_h = mask[:Pe].cpu().pin_memory()
-        for i in range(2):
-            run(args.mode, i, rows=(resp_h, mask_h))
+        fn = step_fn(trainer, args.mode)
+        for _ in range(2):
+            fn(resp_h, mask_h)
         torch.cuda.synchronize()
         ksteps = max(3, min(args.steps, 10))
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(ksteps):
-            o = run(args.mode, i, rows=(resp_h, mask_h))
+        for _ in range(ksteps):
+            o = fn(resp_h, mask_h)
             _ = o.item()
         e1.record()
         torch.cuda.synchronize()
@@ -370,47 +471,35 @@ def main():
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": Pe * I * world * ksteps / (float(ems.item()) * 1e-3), "unit": "cells/s",
                "h2d_bytes_per_step": Pe * I * BYTES_PER_CELL, "d2h_bytes_per_step": 16,
-               "rows_per_step": Pe, "steps": ksteps,
-               "note": "pinned host response/mask -> vibo_fused_elbo_host (chunked H2D overlapped "
-                       "with the kernel) -> loss read back"}
+               "rows_per_step": Pe, "steps": ksteps, "ms_per_step": float(ems.item()) / ksteps,
+               "note": "pinned host response/mask (reference layout, 5 B/cell) -> vibo_fused_elbo_host "
+                       "(chunked H2D overlapped with the kernel) -> loss read back"}
         del resp_h, mask_h
 
     # The other single-GPU BASELINE.json configurations (parity-test cases, not the
     # headline): same step definitions, fewer steps, reported under "other_configs".
-    # They run the multi-pass composition (tensor-core / slab-stream kernels): each
-    # pass streams the 5 B/cell matrix once -> 2 passes per eval, 3 per train step.
+    # frac_of_peak is ALGORITHMIC: P*I*5 bytes / step time / peak, however many passes
+    # over the rows the step makes (passes_over_rows says how many).
     other_configs = {}
     if world == 1 and args.extra_workloads:
+        trainer.close()
         del resp, mask, model, trainer
         torch.cuda.empty_cache()
         for wname in [w for w in args.extra_workloads.split(",") if w and w != args.workload]:
             try:
                 irt2, P2, I2, D2, cond2, miss2, flows2 = WORKLOADS[wname]
-                r2, m2 = synth_rows(P2, I2, D2, irt2, miss2, dev, seed=42)
-                torch.manual_seed(42)
-                cls2 = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[irt2]
-                model2 = cls2(D2, I2, hidden_dim=64, ability_merge="product", conditional_posterior=cond2,
-                              n_norm_flows=flows2).to(dev)
-                tr2 = vdist.ShardedElboTrainer(model2, lr=5e-3, world_size=1, rank=0, person_offset=0,
-                                               use_kl_divergence=(flows2 == 0), cuda_graph=bool(args.cuda_graph))
+                r2, m2, model2, tr2 = make(wname)
                 rec = {"workload": describe(wname), "single_pass_kernel": bool(tr2.uses_fused)}
                 for mode2, passes in (("eval", 2), ("train", 3)):
-                    fn = tr2.eval_step if mode2 == "eval" else tr2.train_step
-                    for i in range(3):
-                        fn(r2, m2, step_index=i)
-                    torch.cuda.synchronize()
-                    k2 = max(3, min(args.steps, 10))
-                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a0.record()
-                    for i in range(k2):
-                        o2 = fn(r2, m2, step_index=3 + i)
-                    a1.record()
-                    torch.cuda.synchronize()
-                    ms2 = a0.elapsed_time(a1) / k2
-                    npass = 1 if tr2.uses_fused else passes
-                    gbs = P2 * I2 * BYTES_PER_CELL * npass / (ms2 * 1e-3) / 1e9
-                    rec[mode2] = {"ms_per_step": ms2, "cells_per_s": P2 * I2 / (ms2 * 1e-3), "loss": float(o2.item()),
-                                  "passes_over_rows": npass, "hbm_gbs_algorithmic": gbs, "frac_of_peak": gbs / peak}
+                    k2 = max(10, min(args.steps, 50))
+                    t2 = time_steps(tr2, mode2, (r2, m2), k2, 3)
+                    ms2 = t2["ms_per_step"]
+                    gbs = P2 * I2 * BYTES_PER_CELL / (ms2 * 1e-3) / 1e9
+                    rec[mode2] = {"ms_per_step": ms2, "cells_per_s": P2 * I2 / (ms2 * 1e-3), "loss": t2["loss"],
+                                  "passes_over_rows": 1 if tr2.uses_fused else passes,
+                                  "hbm_gbs_algorithmic": gbs, "frac_of_peak": gbs / peak,
+                                  "gpu_launches_per_step": t2["gpu_launches"] / k2,
+                                  "cuda_graph": t2["cuda_graph"]}
                 other_configs[wname] = rec
                 del r2, m2, model2, tr2
                 torch.cuda.empty_cache()
@@ -420,7 +509,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_reference_cpu(args.workload, 3, 1, args.mode)
-        cpu_baseline = {"value": r["value"], "unit": "cells/s", "cores": r["cores"], "kind": "port",
+        cpu_baseline = {"value": r["value"], "unit": "cells/s", "cores": r["cores"], "kind": r["kind"],
                         "sample": r["sample"]}
 
     if rank == 0:
@@ -437,10 +526,12 @@ def main():
                            "l2": "inputs (%.2f GB/GPU) >> 126 MB L2, no flush" % (P * I * 5 / 1e9)
                            if P * I * 5 > 4 * 126e6 else "inputs fit L2; no flush (small parity config)",
                            "parallelism": f"person-sharded dp{world}",
+                           "allreduce": ar_kind,
                            "cuda_graph": main_res["cuda_graph"]},
                 "evals_per_sec": main_res["evals_per_sec"], "loss": main_res["loss"],
                 "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": main_res["clocks"],
+                "strong_scaling": strong,
                 "other_configs": other_configs or None,
                 ("train_step" if other_mode == "train" else "eval_step"): other_res}
         print(json.dumps(line))

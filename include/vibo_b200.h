@@ -105,6 +105,27 @@ int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t*
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * vibo_fused_elbo for CUDA-graph replays: the reparameterisation noise is always drawn in-kernel
+ * and the Philox key is read FROM DEVICE MEMORY when the kernel runs:
+ *   key = seed_state[0] + seed_state[1]      (device uint64[2] = {seed, step})
+ * so a captured step draws fresh noise on every replay once the caller bumps seed_state[1]
+ * (the role torch's global generator plays for models.py:509 in the reference loop,
+ * vibo.py:243-268), still keyed by the global person index.
+ */
+int vibo_fused_elbo_graph(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                          const float* table, const float* item_feat, const uint64_t* seed_state,
+                          float beta, double* out_scalars, float* ability_mu, float* ability_logvar,
+                          float* ability, float* g_table, float* g_item, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* The (P, D) standard normals vibo_fused_elbo draws in-kernel when eps_ability is NULL, as a
+ * tensor: Philox4x32-10, counter = (person_offset + row, block), key = seed, or
+ * seed_state[0] + seed_state[1] read on the device when seed_state is non-NULL.  Used by the
+ * composed paths (flows, mean merge) so that their noise is keyed by person too. */
+int vibo_philox_normal(const vibo_desc* desc, uint64_t seed, const uint64_t* seed_state, float* eps,
+                       void* stream);
+
+/*
  * Same computation with response / mask in HOST memory (pinned or pageable):
  * rows are streamed host->device in person chunks on an internal copy stream,
  * overlapped with the kernel on the previous chunk; results (out_scalars and
@@ -229,6 +250,28 @@ int vibo_flow_person_backward(const vibo_desc* desc, int n_flows, const float* a
                               const float* g_term, float* g_ability_mu, float* g_ability_logvar,
                               float* g_uhat, float* g_w, float* g_b, void* workspace,
                               size_t workspace_bytes, void* stream);
+
+/*
+ * Per-step exchange of the person-sharded run (one process per GPU, one node): in-place SUM over
+ * the ranks of a small float buffer ([loss | parameter gradients], the `optimizer.step()` input of
+ * vibo.py:266-268 when persons are split over GPUs).  One kernel over NVLink peer memory (CUDA
+ * IPC), capturable in a CUDA graph; the sum runs in rank order, so all ranks get identical bits.
+ *
+ *   create    allocates this rank's exchange region (device of the calling thread) sized for
+ *             max_floats and writes its VIBO_COMM_HANDLE_BYTES-byte IPC handle to handle_out;
+ *   connect   all_handles = the world_size handles in rank order (exchange them with any host
+ *             collective, e.g. torch.distributed.all_gather_object); barrier afterwards;
+ *   allreduce every rank must issue the same sequence of calls (same n); enqueued on `stream`;
+ *   status    VIBO_OK, or VIBO_ERR_CUDA if a peer failed to arrive within 20 s (synchronises).
+ */
+#define VIBO_COMM_HANDLE_BYTES 64
+typedef struct vibo_comm vibo_comm;
+int vibo_comm_create(int rank, int world_size, size_t max_floats, vibo_comm** out, void* handle_out);
+int vibo_comm_connect(vibo_comm* comm, const void* all_handles);
+int vibo_comm_allreduce(vibo_comm* comm, float* data, size_t n, void* stream);
+int vibo_comm_status(vibo_comm* comm);
+int vibo_comm_destroy(vibo_comm* comm);
+const char* vibo_comm_last_error(void);
 
 /*
  * Measurement hooks (used by bench.py; no effect on results).

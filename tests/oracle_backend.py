@@ -48,13 +48,24 @@ def philox_normals(seed, person_ids, D):
     return out
 
 
+def _seed_int(seed):
+    if isinstance(seed, torch.Tensor):
+        return int(seed[0].item()) + int(seed[1].item())
+    return int(seed)
+
+
+def philox_normal(P, D, seed, person_offset, device):
+    out = philox_normals(_seed_int(seed), [person_offset + i for i in range(P)], D)
+    return torch.from_numpy(out).to(device)
+
+
 def fused_elbo(response, mask, table, item_feat, eps_ability, *, irt_model, conditional,
                missing_policy=0, elbo_form=0, beta=1.0, seed=0, person_offset=0, want_grads=True,
                want_person_outputs=False):
     P = response.shape[0]
     D = table.shape[-1] // 2
     if eps_ability is None:
-        eps = philox_normals(seed, [person_offset + i for i in range(P)], D).astype(np.float64)
+        eps = philox_normals(_seed_int(seed), [person_offset + i for i in range(P)], D).astype(np.float64)
     else:
         eps = _np(eps_ability)
     r = KS.fused_elbo(_np(response), _np(mask, np.uint8), _np(table), _np(item_feat), eps,
@@ -113,5 +124,5 @@ def install(monkeypatch):
     import vibo_b200
     K = vibo_b200.kernels
     for name in ("fused_elbo", "encode", "encode_backward", "link_loglik", "decode",
-                 "bernoulli_loglik", "_check_rows"):
+                 "bernoulli_loglik", "_check_rows", "philox_normal"):
         monkeypatch.setattr(K, name, globals()[name])

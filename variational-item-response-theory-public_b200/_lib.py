@@ -41,6 +41,9 @@ SIGNATURES = {
     "vibo_workspace_bytes": (C.c_size_t, [_PD]),
     "vibo_fused_elbo": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_uint64, C.c_float, _p, _p, _p, _p, _p,
                                   _p, _p, C.c_size_t, _p]),
+    "vibo_fused_elbo_graph": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p, _p, _p,
+                                        C.c_size_t, _p]),
+    "vibo_philox_normal": (C.c_int, [_PD, C.c_uint64, _p, _p, _p]),
     "vibo_host_staging_bytes": (C.c_size_t, [_PD, C.c_int64]),
     "vibo_fused_elbo_host": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_uint64, C.c_float, _p, _p, _p, _p,
                                        C.c_int64, _p, C.c_size_t, _p, C.c_size_t, _p]),
@@ -54,6 +57,12 @@ SIGNATURES = {
     "vibo_param_backward": (C.c_int, [_PD, C.c_int] + [_p] * 18),
     "vibo_flow_person_forward": (C.c_int, [_PD, C.c_int] + [_p] * 9 + [_p, C.c_size_t, _p]),
     "vibo_flow_person_backward": (C.c_int, [_PD, C.c_int] + [_p] * 13 + [_p, C.c_size_t, _p]),
+    "vibo_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), _p]),
+    "vibo_comm_connect": (C.c_int, [_p, _p]),
+    "vibo_comm_allreduce": (C.c_int, [_p, _p, C.c_size_t, _p]),
+    "vibo_comm_status": (C.c_int, [_p]),
+    "vibo_comm_destroy": (C.c_int, [_p]),
+    "vibo_comm_last_error": (C.c_char_p, []),
     "vibo_single_pass": (C.c_int, [_PD]),
     "vibo_launch_count": (C.c_uint64, []),
     "vibo_profile_begin": (C.c_int, []),

@@ -114,11 +114,11 @@ size_t vibo_workspace_bytes(const vibo_desc* desc) {
   return a > b ? a : b;
 }
 
-int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t* mask,
-                    const float* table, const float* item_feat, const float* eps_ability,
-                    uint64_t seed, float beta, double* out_scalars, float* ability_mu,
-                    float* ability_logvar, float* ability, float* g_table, float* g_item,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+static int fused_elbo_impl(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                           const float* table, const float* item_feat, const float* eps_ability,
+                           uint64_t seed, const uint64_t* seed_dev, float beta, double* out_scalars,
+                           float* ability_mu, float* ability_logvar, float* ability, float* g_table,
+                           float* g_item, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = check_desc(desc)) return rc;
   if (!response || !mask || !table || !item_feat || !out_scalars)
     return fail(VIBO_ERR_BAD_ARGUMENT, "response, mask, table, item_feat and out_scalars are required");
@@ -140,7 +140,7 @@ int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t*
     return VIBO_OK;
   }
   if (vibo::fused_supported(d, response, mask)) {
-    VIBO_CUDA(vibo::launch_fused(d, response, mask, table, item_feat, eps_ability, seed, beta,
+    VIBO_CUDA(vibo::launch_fused(d, response, mask, table, item_feat, eps_ability, seed, seed_dev, beta,
                                  out_scalars, ability_mu, ability_logvar, ability, g_table, g_item,
                                  workspace, workspace_bytes, false, st),
               "fused kernel");
@@ -169,7 +169,7 @@ int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t*
   if (!ws.ok()) return fail(VIBO_ERR_WORKSPACE, "workspace carve overflow");
 
   VIBO_CUDA(vibo::launch_encode(d, response, mask, table, amu, alv, S, st), "encode");
-  VIBO_CUDA(vibo::launch_person_forward(d, amu, alv, eps_ability, seed,
+  VIBO_CUDA(vibo::launch_person_forward(d, amu, alv, eps_ability, seed, seed_dev,
                                         eps_ability ? nullptr : eps_buf, th, part_term,
                                         out_scalars + 1, st),
             "person_forward");
@@ -184,6 +184,38 @@ int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t*
     VIBO_CUDA(vibo::launch_encode_bwd(d, response, mask, table, amu, S, g_mu, g_lv, g_table, part_ab, st),
               "encode_backward");
   }
+  return VIBO_OK;
+}
+
+int vibo_fused_elbo(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                    const float* table, const float* item_feat, const float* eps_ability,
+                    uint64_t seed, float beta, double* out_scalars, float* ability_mu,
+                    float* ability_logvar, float* ability, float* g_table, float* g_item,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  return fused_elbo_impl(desc, response, mask, table, item_feat, eps_ability, seed, nullptr, beta,
+                         out_scalars, ability_mu, ability_logvar, ability, g_table, g_item, workspace,
+                         workspace_bytes, stream);
+}
+
+int vibo_fused_elbo_graph(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                          const float* table, const float* item_feat, const uint64_t* seed_state,
+                          float beta, double* out_scalars, float* ability_mu, float* ability_logvar,
+                          float* ability, float* g_table, float* g_item, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (seed_state == nullptr) return fail(VIBO_ERR_BAD_ARGUMENT, "seed_state is required");
+  return fused_elbo_impl(desc, response, mask, table, item_feat, nullptr, 0, seed_state, beta,
+                         out_scalars, ability_mu, ability_logvar, ability, g_table, g_item, workspace,
+                         workspace_bytes, stream);
+}
+
+int vibo_philox_normal(const vibo_desc* desc, uint64_t seed, const uint64_t* seed_state, float* eps,
+                       void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!eps) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (desc->num_person == 0) return VIBO_OK;
+  VIBO_CUDA(vibo::launch_philox_fill(desc->num_person, desc->ability_dim, desc->person_offset, seed,
+                                     seed_state, eps, static_cast<cudaStream_t>(stream)),
+            "philox_fill");
   return VIBO_OK;
 }
 

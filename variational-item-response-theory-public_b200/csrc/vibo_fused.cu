@@ -73,18 +73,6 @@ FusedPlan fused_plan(const vibo_desc& d) {
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
-__global__ void philox_fill_kernel(int64_t P, int D, int64_t person_offset, uint64_t seed,
-                                   float* __restrict__ eps) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float nrm[4];
-    for (int d = 0; d < D; ++d) {
-      if ((d & 3) == 0) philox_normal4(seed, (uint64_t)(person_offset + i), (uint32_t)(d >> 2), nrm);
-      eps[i * D + d] = nrm[d & 3];
-    }
-  }
-}
-
 // Sum the per-CTA partials in a fixed order; apply the expert chain rule and
 // the sign convention g = d loss_k / d (.) with loss_k = -LL + ...
 // Block = 32 outputs x 8 partial-slices: each thread sums every 8th partial
@@ -202,9 +190,9 @@ size_t fused_workspace_bytes(const vibo_desc& d) {
 
 cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* mask,
                          const float* table, const float* item_feat, const float* eps,
-                         uint64_t seed, float beta, double* out_scalars, float* amu, float* alv,
-                         float* ability, float* g_table, float* g_item, void* ws, size_t ws_bytes,
-                         bool accumulate, cudaStream_t st) {
+                         uint64_t seed, const uint64_t* seed_dev, float beta, double* out_scalars,
+                         float* amu, float* alv, float* ability, float* g_table, float* g_item, void* ws,
+                         size_t ws_bytes, bool accumulate, cudaStream_t st) {
   const FusedPlan pl = fused_plan(d);
   if (!pl.ok) return cudaErrorNotSupported;
   if (ws_bytes < fused_workspace_bytes(d)) return cudaErrorInvalidValue;
@@ -216,13 +204,8 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   float* part_table = reinterpret_cast<float*>(base + off);    off += align256(G * 4 * D * sizeof(float));
   float* part_item = reinterpret_cast<float*>(base + off);     off += align256(G * (size_t)d.num_item * F * sizeof(float));
   float* eps_buf = reinterpret_cast<float*>(base + off);
-  if (eps == nullptr) {
-    int64_t blocks = (d.num_person + 255) / 256;
-    if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-    philox_fill_kernel<<<(int)blocks, 256, 0, st>>>(d.num_person, D, d.person_offset, seed, eps_buf);
-    note_launch();
-    eps = eps_buf;
-  } else if (reinterpret_cast<uintptr_t>(eps) & 15) {
+  // eps == nullptr: the noise is drawn inside the fused kernel (Philox keyed by person)
+  if (eps != nullptr && (reinterpret_cast<uintptr_t>(eps) & 15)) {
     cudaError_t e = cudaMemcpyAsync(eps_buf, eps, (size_t)d.num_person * D * sizeof(float),
                                     cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
@@ -233,6 +216,7 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   p.P = d.num_person; p.I = d.num_item; p.R = pl.R; p.nstage = pl.nstage; p.form = d.elbo_form;
   p.missing_policy = d.missing_policy; p.beta = beta;
   { const char* dbg = getenv("VIBO_FUSED_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; } p.resp = resp; p.mask = mask; p.eps = eps;
+  p.seed = seed; p.seed_dev = seed_dev; p.person_offset = d.person_offset;
   p.item_feat = item_feat; p.table = table;
   const bool person_out = amu != nullptr && alv != nullptr && ability != nullptr;
   p.out_mu = person_out ? amu : nullptr; p.out_lv = person_out ? alv : nullptr;

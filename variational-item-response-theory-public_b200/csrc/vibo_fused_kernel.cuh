@@ -51,7 +51,10 @@ struct FusedParams {
   int debug;    // 0 normal; 1 stream only (no math); 2 math only (no refills)  [VIBO_FUSED_DEBUG]
   const float* resp;
   const uint8_t* mask;
-  const float* eps;        // (P, D)
+  const float* eps;        // (P, D), or null: draw in-kernel (Philox keyed by seed, person_offset + row)
+  uint64_t seed;           // Philox key when seed_dev is null
+  const uint64_t* seed_dev;  // device {seed, step}: key = seed + step, read at run time (CUDA-graph replays)
+  int64_t person_offset;   // global index of row 0
   const float* item_feat;  // (I, F)
   const float* table;      // (2, 1, 2D)
   float* out_mu;           // (P, D) or null
@@ -154,13 +157,31 @@ __device__ __forceinline__ void fused_issue_chunk(const FusedParams& p, const Fu
   const int I = p.I, R = p.R;
   const int64_t row0 = c * R;
   const int rows = (int)((p.P - row0 < R) ? p.P - row0 : R);
-  const uint32_t b_resp = (uint32_t)rows * I * 4, b_mask = (uint32_t)rows * I, b_eps = (uint32_t)rows * D * 4;
+  const uint32_t b_resp = (uint32_t)rows * I * 4, b_mask = (uint32_t)rows * I;
+  const bool draw = p.eps == nullptr;
+  const uint32_t b_eps = draw ? 0u : (uint32_t)rows * D * 4;
+  if (draw) {
+    // reparameterisation noise drawn here (models.py:506-510 randn_like), one lane per person of
+    // the chunk, keyed by the GLOBAL person index: written with ordinary shared stores that the
+    // release of the mbarrier arrive below (after __syncwarp) publishes to the consumer warps
+    const uint64_t key = p.seed_dev != nullptr ? p.seed_dev[0] + p.seed_dev[1] : p.seed;
+    float* se = reinterpret_cast<float*>(st + L.eps_off);
+    for (int r = lane; r < rows; r += 32) {
+      float nrm[4];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if ((d & 3) == 0) philox_normal4(key, (uint64_t)(p.person_offset + row0 + r), (uint32_t)(d >> 2), nrm);
+        se[r * D + d] = nrm[d & 3];
+      }
+    }
+    __syncwarp();
+  }
   if (((b_mask | b_eps) & 15u) == 0) {
     if (lane == 0) {
       mbar_expect_tx(bar, b_resp + b_mask + b_eps);
       bulk_g2s(st, p.resp + row0 * I, b_resp, bar);
       bulk_g2s(st + L.mask_off, p.mask + row0 * I, b_mask, bar);
-      bulk_g2s(st + L.eps_off, p.eps + row0 * D, b_eps, bar);
+      if (!draw) bulk_g2s(st + L.eps_off, p.eps + row0 * D, b_eps, bar);
     }
   } else {
     // ragged tail chunk: sizes are not 16-byte multiples, copy by hand
@@ -170,9 +191,11 @@ __device__ __forceinline__ void fused_issue_chunk(const FusedParams& p, const Fu
     const uint8_t* gm = p.mask + row0 * I;
     uint8_t* sm = st + L.mask_off;
     for (int k = lane; k < rows * I; k += 32) sm[k] = gm[k];
-    const float* ge = p.eps + row0 * D;
-    float* se = reinterpret_cast<float*>(st + L.eps_off);
-    for (int k = lane; k < rows * D; k += 32) se[k] = ge[k];
+    if (!draw) {
+      const float* ge = p.eps + row0 * D;
+      float* se = reinterpret_cast<float*>(st + L.eps_off);
+      for (int k = lane; k < rows * D; k += 32) se[k] = ge[k];
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
   }

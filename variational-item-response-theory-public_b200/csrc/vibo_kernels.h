@@ -53,13 +53,15 @@ cudaError_t stream_encode_bwd(const vibo_desc& d, const float* resp, const uint8
 // multi-pass composition of vibo_fused_elbo.
 int person_grid(int64_t P);
 cudaError_t launch_person_forward(const vibo_desc& d, const float* amu, const float* alv,
-                                  const float* eps_or_null, uint64_t seed, float* eps_out,
-                                  float* ability, double* part_term, double* out_term,
+                                  const float* eps_or_null, uint64_t seed, const uint64_t* seed_dev,
+                                  float* eps_out, float* ability, double* part_term, double* out_term,
                                   cudaStream_t st);
 cudaError_t launch_person_backward(const vibo_desc& d, float beta, const float* amu,
                                    const float* alv, const float* eps, const float* ability,
                                    const float* g_ll_ability, float* g_mu, float* g_lv,
                                    cudaStream_t st);
+cudaError_t launch_philox_fill(int64_t P, int D, int64_t person_offset, uint64_t seed,
+                               const uint64_t* seed_dev, float* eps, cudaStream_t st);
 cudaError_t launch_negate(float* v, int n, cudaStream_t st);
 int flow_grid(int64_t P);
 cudaError_t launch_flow_person_forward(int64_t P, int D, int K, const float* amu, const float* alv,
@@ -93,8 +95,8 @@ bool fused_supported(const vibo_desc& d, const float* resp, const uint8_t* mask)
 size_t fused_workspace_bytes(const vibo_desc& d);
 cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* mask,
                          const float* table, const float* item_feat, const float* eps,
-                         uint64_t seed, float beta, double* out_scalars, float* amu, float* alv,
-                         float* ability, float* g_table, float* g_item, void* ws, size_t ws_bytes,
-                         bool accumulate, cudaStream_t st);
+                         uint64_t seed, const uint64_t* seed_dev, float beta, double* out_scalars,
+                         float* amu, float* alv, float* ability, float* g_table, float* g_item, void* ws,
+                         size_t ws_bytes, bool accumulate, cudaStream_t st);
 
 }  // namespace vibo

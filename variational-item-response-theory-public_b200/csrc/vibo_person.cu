@@ -13,9 +13,10 @@ namespace vibo {
 __global__ void person_forward_kernel(int64_t P, int D, int form, int64_t person_offset,
                                       const float* __restrict__ amu, const float* __restrict__ alv,
                                       const float* __restrict__ eps_in, uint64_t seed,
-                                      float* __restrict__ eps_out, float* __restrict__ ability,
+                                      const uint64_t* __restrict__ seed_dev, float* __restrict__ eps_out, float* __restrict__ ability,
                                       double* __restrict__ part_term) {
   double acc = 0.0;
+  if (seed_dev != nullptr) seed = seed_dev[0] + seed_dev[1];  // {seed, step} in device memory (graph replays)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
        i += (int64_t)gridDim.x * blockDim.x) {
     float nrm[4];
@@ -92,6 +93,28 @@ __global__ void person_backward_kernel(int64_t n, int form, float beta, const fl
   }
 }
 
+// Standard normals keyed by (seed, person_offset + row): the same stream the fused kernels draw
+// in-kernel, for the composed paths (flows, mean merge) that need eps as a tensor.
+__global__ void philox_fill_kernel(int64_t P, int D, int64_t person_offset, uint64_t seed,
+                                   const uint64_t* __restrict__ seed_dev, float* __restrict__ eps) {
+  if (seed_dev != nullptr) seed = seed_dev[0] + seed_dev[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float nrm[4];
+    for (int d = 0; d < D; ++d) {
+      if ((d & 3) == 0) philox_normal4(seed, (uint64_t)(person_offset + i), (uint32_t)(d >> 2), nrm);
+      eps[i * D + d] = nrm[d & 3];
+    }
+  }
+}
+
+cudaError_t launch_philox_fill(int64_t P, int D, int64_t person_offset, uint64_t seed,
+                               const uint64_t* seed_dev, float* eps, cudaStream_t st) {
+  philox_fill_kernel<<<person_grid(P), 256, 0, st>>>(P, D, person_offset, seed, seed_dev, eps);
+  note_launch();
+  return cudaGetLastError();
+}
+
 __global__ void negate_kernel(float* v, int n) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) v[k] = -v[k];
 }
@@ -121,12 +144,12 @@ int person_grid(int64_t P) {
 }
 
 cudaError_t launch_person_forward(const vibo_desc& d, const float* amu, const float* alv,
-                                  const float* eps_or_null, uint64_t seed, float* eps_out,
-                                  float* ability, double* part_term, double* out_term,
+                                  const float* eps_or_null, uint64_t seed, const uint64_t* seed_dev,
+                                  float* eps_out, float* ability, double* part_term, double* out_term,
                                   cudaStream_t st) {
   const int grid = person_grid(d.num_person);
   person_forward_kernel<<<grid, 256, 0, st>>>(d.num_person, d.ability_dim, d.elbo_form,
-                                              d.person_offset, amu, alv, eps_or_null, seed, eps_out,
+                                              d.person_offset, amu, alv, eps_or_null, seed, seed_dev, eps_out,
                                               ability, part_term);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -58,7 +58,9 @@ def fused_elbo(response, mask, table, item_feat, eps_ability, *, irt_model, cond
                missing_policy=MISSING_PRIOR, elbo_form=ELBO_KL, beta=1.0, seed=0, person_offset=0,
                want_grads=True, want_person_outputs=False):
     """vibo_fused_elbo.  Returns dict(scalars (2,) f64 [LL, person_term],
-    g_table, g_item (or None), ability_mu/ability_logvar/ability (or None))."""
+    g_table, g_item (or None), ability_mu/ability_logvar/ability (or None)).
+    ``seed`` may be a device int64 tensor {seed, step} (vibo_fused_elbo_graph): the Philox key is
+    then read on the device when the kernel runs, so CUDA-graph replays draw fresh noise."""
     _check_rows(response, mask)
     lib = _lib.load()
     P, I = response.shape
@@ -81,11 +83,19 @@ def fused_elbo(response, mask, table, item_feat, eps_ability, *, irt_model, cond
         alv = torch.empty_like(amu)
         th = torch.empty_like(amu)
     ws = workspace(desc, dev)
-    rc = lib.vibo_fused_elbo(C.byref(desc), _ptr(response), _ptr(mask), _ptr(table), _ptr(item_feat),
-                             _ptr(eps_ability), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(beta),
-                             _ptr(scalars), _ptr(amu), _ptr(alv), _ptr(th), _ptr(g_table), _ptr(g_item),
-                             _ptr(ws), ws.numel(), _stream(dev))
-    _lib.check(rc, "vibo_fused_elbo")
+    if isinstance(seed, torch.Tensor):
+        assert eps_ability is None and seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 2
+        rc = lib.vibo_fused_elbo_graph(C.byref(desc), _ptr(response), _ptr(mask), _ptr(table), _ptr(item_feat),
+                                       _ptr(seed), C.c_float(beta), _ptr(scalars), _ptr(amu), _ptr(alv),
+                                       _ptr(th), _ptr(g_table), _ptr(g_item), _ptr(ws), ws.numel(),
+                                       _stream(dev))
+        _lib.check(rc, "vibo_fused_elbo_graph")
+    else:
+        rc = lib.vibo_fused_elbo(C.byref(desc), _ptr(response), _ptr(mask), _ptr(table), _ptr(item_feat),
+                                 _ptr(eps_ability), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(beta),
+                                 _ptr(scalars), _ptr(amu), _ptr(alv), _ptr(th), _ptr(g_table), _ptr(g_item),
+                                 _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(rc, "vibo_fused_elbo")
     return dict(scalars=scalars, g_table=g_table, g_item=g_item, ability_mu=amu,
                 ability_logvar=alv, ability=th)
 
@@ -291,3 +301,19 @@ def person_counts(response, mask):
                                         _stream(response.device))
     _lib.check(rc, "vibo_person_counts")
     return counts
+
+
+def philox_normal(P, D, seed, person_offset, device):
+    """vibo_philox_normal -> (P, D) float32: the noise the fused kernels draw in-kernel for
+    (seed, person_offset).  ``seed`` is an int or a device int64 {seed, step} tensor."""
+    if torch.device(device).type != "cuda":
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    desc = make_desc(P, 1, D, 2, False, person_offset=person_offset)
+    out = torch.empty(P, D, dtype=torch.float32, device=device)
+    if isinstance(seed, torch.Tensor):
+        rc = _lib.load().vibo_philox_normal(C.byref(desc), C.c_uint64(0), _ptr(seed), _ptr(out), _stream(device))
+    else:
+        rc = _lib.load().vibo_philox_normal(C.byref(desc), C.c_uint64(int(seed) & (2 ** 64 - 1)), None, _ptr(out),
+                                            _stream(device))
+    _lib.check(rc, "vibo_philox_normal")
+    return out

@@ -352,7 +352,7 @@ class VIBO_1PL(nn.Module):
         # unconditional model on the GPU: the whole parameter-side chain is two small kernels
         if self.ability_merge == 'mean':
             item_feat = eps_item * torch.exp(0.5 * item_feat_logvar) + item_feat_mu
-            if eps_ability is None:
+            if eps_ability is None and seed is None:
                 eps_ability = torch.randn(P, self.ability_dim, dtype=torch.float32, device=resp.device)
             return self._composed_elbo(resp, msk, None, item_feat, item_feat_mu, item_feat_logvar, eps_ability,
                                        seed, person_offset, item_term_scale, return_outputs,
@@ -380,7 +380,8 @@ class VIBO_1PL(nn.Module):
         cfg = dict(irt_model=self.irt_num, conditional=self.conditional_posterior,
                    missing_policy=self.ability_encoder.missing_policy,
                    elbo_form=VF.ELBO_KL if use_kl_divergence else VF.ELBO_SAMPLE, beta=beta,
-                   seed=0 if seed is None else int(seed), person_offset=int(person_offset),
+                   seed=0 if seed is None else (seed if isinstance(seed, torch.Tensor) else int(seed)),
+                   person_offset=int(person_offset),
                    want_person_outputs=return_outputs)
         if host_rows:
             cfg["chunk_person"] = getattr(self, "host_chunk_person", 65536)
@@ -419,8 +420,8 @@ class VIBO_1PL(nn.Module):
         else:
             a_mu, a_lv = VF.EncodePosterior.apply(resp, msk, table, enc.conditional, enc.missing_policy)
         if eps_ability is None:
-            g = torch.Generator(device=resp.device).manual_seed(int(seed) + int(person_offset))
-            eps_ability = torch.randn(a_mu.shape, generator=g, device=resp.device)
+            # the noise the fused kernels draw in-kernel: Philox keyed by (seed, global person index)
+            eps_ability = VF.K.philox_normal(a_mu.shape[0], a_mu.shape[1], seed, int(person_offset), resp.device)
         outputs = dict(ability_mu=a_mu, ability_logvar=a_lv, item_feat=item_feat, item_feat_mu=item_feat_mu,
                        item_feat_logvar=item_feat_logvar)
         if self.n_norm_flows > 0:
