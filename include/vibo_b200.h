@@ -286,6 +286,10 @@ const char* vibo_comm_last_error(void);
  *                          0 if it composes the general kernels.
  */
 int vibo_single_pass(const vibo_desc* desc);
+/* Largest num_item any entry point accepts for desc->ability_dim (2048 for D <= 4, 1024 above):
+ * item slabs live in registers of at most 16 warps.  0 if ability_dim is unsupported.  Callers
+ * (module constructor, CLI) check this up front instead of failing at the first step. */
+int vibo_max_items(const vibo_desc* desc);
 uint64_t vibo_launch_count(void);
 int vibo_profile_begin(void);
 int vibo_profile_end(int* n_launches, double* total_ms);

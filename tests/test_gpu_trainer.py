@@ -51,6 +51,16 @@ def test_trainer_steps_match_oracle_adam(name, irt, D, I, cond, P, miss, graph):
     from vibo_b200.distributed import ShardedElboTrainer
     dev = torch.device("cuda:0")
     model = _model(irt, D, I, cond, dev)
+    if irt == 3:
+        # A fresh N(0,1) 3PL D=5 item table is a SATURATING state: thousands of cells sit on the
+        # eps32 clamp (zero gradient outside), where the fp32 reference itself is a knife edge
+        # (fp32 vs fp64 reference: 2e-3 on the loss).  Multi-step Adam parity is only
+        # meaningful off the clamp, so the item posterior is pulled in (reference fp32 vs fp64
+        # then agree to 1e-7 over these 3 steps); the clamp itself is pinned by
+        # test_saturated_cells and the m2pl_d1_unc_saturating fixture.
+        with torch.no_grad():
+            model.item_encoder.mu_lookup.weight.mul_(0.3)
+            model.item_encoder.logvar_lookup.weight.mul_(0.1).sub_(3.0)
     params = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     resp, mask = _rows(P, I, miss, seed=11)
     resp_d, mask_d = resp.to(dev), mask.to(dev)

@@ -64,6 +64,7 @@ SIGNATURES = {
     "vibo_comm_destroy": (C.c_int, [_p]),
     "vibo_comm_last_error": (C.c_char_p, []),
     "vibo_single_pass": (C.c_int, [_PD]),
+    "vibo_max_items": (C.c_int, [_PD]),
     "vibo_launch_count": (C.c_uint64, []),
     "vibo_profile_begin": (C.c_int, []),
     "vibo_profile_end": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_double)]),

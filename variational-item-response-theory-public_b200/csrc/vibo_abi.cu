@@ -84,12 +84,18 @@ size_t general_workspace_bytes(const vibo_desc* d) {
 }  // namespace
 
 namespace vibo {
+int set_last_error(int code, const char* msg) { return fail(code, msg); }
 int item_width_host(int model, int D) { return model == 1 ? 1 : (model == 2 ? D + 1 : D + 2); }
 }  // namespace vibo
 
 extern "C" {
 
 int vibo_version(void) { return VIBO_B200_VERSION; }
+
+int vibo_max_items(const vibo_desc* desc) {
+  if (desc == nullptr || desc->ability_dim < 1 || desc->ability_dim > VIBO_MAX_ABILITY_DIM) return 0;
+  return vibo::general_max_items(desc->ability_dim);
+}
 
 int vibo_single_pass(const vibo_desc* desc) {
   if (check_desc(desc) != VIBO_OK) return 0;

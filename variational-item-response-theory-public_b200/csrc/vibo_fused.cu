@@ -1,6 +1,7 @@
 // Dispatch, workspace carving and finalisation of the single-pass fused ELBO
 // kernel (vibo_fused_kernel.cuh).
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "vibo_fused2_kernel.cuh"
@@ -50,8 +51,11 @@ FusedPlan fused_plan(const vibo_desc& d) {
   int ns = two_phase ? 3 : 4;  // at most 16 mbarriers per CTA
   const size_t budget = two_phase ? kSmemCap : kSmemBudget;
   FusedSmem L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch(R, ns));
-  while (ns > 2 && L.total > budget) {
-    --ns;
+  // too large for shared memory (narrow rows make r_min-multiples big): first shorter stages at
+  // full ring depth, then a shallower ring
+  while (L.total > budget && (R > r_min || ns > 2)) {
+    if (R > r_min) R -= r_min;
+    else --ns;
     L = fused_smem_layout(I, D, d.irt_model, R, ns, n_teams, scratch(R, ns));
   }
   if (L.total > budget) return pl;
@@ -142,17 +146,21 @@ fused_finalize_kernel(int nparts, int I, int F, int DA, int D, bool grad, bool a
 
 // ---- measurement hooks (vibo_profile_begin / vibo_profile_end) -------------
 struct EventPair { cudaEvent_t a, b; };
+// process-wide (a bench harness brackets launches made from any thread); guarded by g_prof_mutex
+std::mutex g_prof_mutex;
 bool g_profiling = false;
 std::vector<EventPair> g_events;
 
 }  // namespace
 
 void profile_begin() {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_events.clear();
   g_profiling = true;
 }
 
 int profile_end(int* n, double* total_ms) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_profiling = false;
   double tot = 0.0;
   int cnt = 0;
@@ -204,8 +212,12 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   float* part_table = reinterpret_cast<float*>(base + off);    off += align256(G * 4 * D * sizeof(float));
   float* part_item = reinterpret_cast<float*>(base + off);     off += align256(G * (size_t)d.num_item * F * sizeof(float));
   float* eps_buf = reinterpret_cast<float*>(base + off);
-  // eps == nullptr: the noise is drawn inside the fused kernel (Philox keyed by person)
-  if (eps != nullptr && (reinterpret_cast<uintptr_t>(eps) & 15)) {
+  float* eps_draw = nullptr;
+  if (eps == nullptr) {
+    // the fused kernel draws the noise itself (Philox keyed by person) into this scratch
+    eps_draw = eps_buf;
+    eps = eps_buf;
+  } else if (reinterpret_cast<uintptr_t>(eps) & 15) {
     cudaError_t e = cudaMemcpyAsync(eps_buf, eps, (size_t)d.num_person * D * sizeof(float),
                                     cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
@@ -216,14 +228,19 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   p.P = d.num_person; p.I = d.num_item; p.R = pl.R; p.nstage = pl.nstage; p.form = d.elbo_form;
   p.missing_policy = d.missing_policy; p.beta = beta;
   { const char* dbg = getenv("VIBO_FUSED_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; } p.resp = resp; p.mask = mask; p.eps = eps;
-  p.seed = seed; p.seed_dev = seed_dev; p.person_offset = d.person_offset;
+  p.eps_draw = eps_draw; p.seed = seed; p.seed_dev = seed_dev; p.person_offset = d.person_offset;
   p.item_feat = item_feat; p.table = table;
   const bool person_out = amu != nullptr && alv != nullptr && ability != nullptr;
   p.out_mu = person_out ? amu : nullptr; p.out_lv = person_out ? alv : nullptr;
   p.out_theta = person_out ? ability : nullptr;
   p.part_scalar = part_scalar; p.part_table = part_table; p.part_item = part_item;
   EventPair ev{nullptr, nullptr};
-  if (g_profiling) {
+  bool profiling;
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    profiling = g_profiling;
+  }
+  if (profiling) {
     cudaEventCreate(&ev.a);
     cudaEventCreate(&ev.b);
     cudaEventRecord(ev.a, st);
@@ -236,8 +253,9 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   } else if (d.irt_model == 3 && D == 1) {
     e = launch_fused_md<3, 1>(p, pl.grid, pl.smem, grad, st);
   }
-  if (g_profiling) {
+  if (profiling) {
     cudaEventRecord(ev.b, st);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     g_events.push_back(ev);
   }
   if (e != cudaSuccess) return e;

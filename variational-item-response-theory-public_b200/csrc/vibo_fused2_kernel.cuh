@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 16) s_max[threadIdx.x] = 0.0f;
+  fused_draw_noise<D>(p, NQ);
   __syncthreads();
   {
     float amax[DA > 0 ? DA : 1], bmax = 0.0f;
@@ -711,21 +712,16 @@ cudaError_t launch_fused2_md(const FusedParams& p, int grid, size_t smem, bool g
 
 template <int MODEL, int D, int LPP, int NG>
 static cudaError_t launch_fused2_cfg(const FusedParams& p, int grid, size_t smem, bool grad, cudaStream_t st) {
-  static size_t smem_set[2] = {0, 0};
+  // the opt-in to > 48 KB dynamic shared memory is per device and per function: set it on every
+  // launch (a host-side attribute write, ~1 us) instead of caching it in process-wide state
   cudaError_t e;
   if (grad) {
     auto k = fused2_kernel<MODEL, D, LPP, NG, true>;
-    if (smem > smem_set[1]) {
-      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      smem_set[1] = smem;
-    }
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<grid, kF2Threads, smem, st>>>(p);
   } else {
     auto k = fused2_kernel<MODEL, D, LPP, NG, false>;
-    if (smem > smem_set[0]) {
-      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      smem_set[0] = smem;
-    }
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<grid, kF2Threads, smem, st>>>(p);
   }
   return cudaGetLastError();

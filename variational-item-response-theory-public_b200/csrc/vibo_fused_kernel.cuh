@@ -51,7 +51,8 @@ struct FusedParams {
   int debug;    // 0 normal; 1 stream only (no math); 2 math only (no refills)  [VIBO_FUSED_DEBUG]
   const float* resp;
   const uint8_t* mask;
-  const float* eps;        // (P, D), or null: draw in-kernel (Philox keyed by seed, person_offset + row)
+  const float* eps;        // (P, D) standard normals the rows are staged from
+  float* eps_draw;         // non-null: == eps, a scratch this kernel FILLS first (fused_draw_noise)
   uint64_t seed;           // Philox key when seed_dev is null
   const uint64_t* seed_dev;  // device {seed, step}: key = seed + step, read at run time (CUDA-graph replays)
   int64_t person_offset;   // global index of row 0
@@ -157,31 +158,13 @@ __device__ __forceinline__ void fused_issue_chunk(const FusedParams& p, const Fu
   const int I = p.I, R = p.R;
   const int64_t row0 = c * R;
   const int rows = (int)((p.P - row0 < R) ? p.P - row0 : R);
-  const uint32_t b_resp = (uint32_t)rows * I * 4, b_mask = (uint32_t)rows * I;
-  const bool draw = p.eps == nullptr;
-  const uint32_t b_eps = draw ? 0u : (uint32_t)rows * D * 4;
-  if (draw) {
-    // reparameterisation noise drawn here (models.py:506-510 randn_like), one lane per person of
-    // the chunk, keyed by the GLOBAL person index: written with ordinary shared stores that the
-    // release of the mbarrier arrive below (after __syncwarp) publishes to the consumer warps
-    const uint64_t key = p.seed_dev != nullptr ? p.seed_dev[0] + p.seed_dev[1] : p.seed;
-    float* se = reinterpret_cast<float*>(st + L.eps_off);
-    for (int r = lane; r < rows; r += 32) {
-      float nrm[4];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        if ((d & 3) == 0) philox_normal4(key, (uint64_t)(p.person_offset + row0 + r), (uint32_t)(d >> 2), nrm);
-        se[r * D + d] = nrm[d & 3];
-      }
-    }
-    __syncwarp();
-  }
+  const uint32_t b_resp = (uint32_t)rows * I * 4, b_mask = (uint32_t)rows * I, b_eps = (uint32_t)rows * D * 4;
   if (((b_mask | b_eps) & 15u) == 0) {
     if (lane == 0) {
       mbar_expect_tx(bar, b_resp + b_mask + b_eps);
       bulk_g2s(st, p.resp + row0 * I, b_resp, bar);
       bulk_g2s(st + L.mask_off, p.mask + row0 * I, b_mask, bar);
-      if (!draw) bulk_g2s(st + L.eps_off, p.eps + row0 * D, b_eps, bar);
+      bulk_g2s(st + L.eps_off, p.eps + row0 * D, b_eps, bar);
     }
   } else {
     // ragged tail chunk: sizes are not 16-byte multiples, copy by hand
@@ -191,14 +174,44 @@ __device__ __forceinline__ void fused_issue_chunk(const FusedParams& p, const Fu
     const uint8_t* gm = p.mask + row0 * I;
     uint8_t* sm = st + L.mask_off;
     for (int k = lane; k < rows * I; k += 32) sm[k] = gm[k];
-    if (!draw) {
-      const float* ge = p.eps + row0 * D;
-      float* se = reinterpret_cast<float*>(st + L.eps_off);
-      for (int k = lane; k < rows * D; k += 32) se[k] = ge[k];
-    }
+    const float* ge = p.eps + row0 * D;
+    float* se = reinterpret_cast<float*>(st + L.eps_off);
+    for (int k = lane; k < rows * D; k += 32) se[k] = ge[k];
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
   }
+}
+
+// In-kernel reparameterisation noise (models.py:506-510 randn_like): before its first bulk copy a
+// CTA fills the scratch rows IT will stage -- chunks (blockIdx.x * NQ + t) + k * gridDim.x * NQ of
+// its NQ teams -- with Philox normals keyed by the GLOBAL person index, all threads in parallel
+// (one person per thread at a time), and then reads them back through the same TMA path as
+// caller-supplied noise.  No separate launch; the 4 D bytes per person stay in L2.  Generic-proxy
+// stores followed by async-proxy (bulk copy) loads: every writer issues fence.proxy.async before
+// the CTA barrier that precedes the first copy.
+template <int D>
+__device__ __forceinline__ void fused_draw_noise(const FusedParams& p, int NQ) {
+  if (p.eps_draw == nullptr) return;
+  const uint64_t key = p.seed_dev != nullptr ? p.seed_dev[0] + p.seed_dev[1] : p.seed;
+  const int R = p.R;
+  const int64_t n_chunks = (p.P + R - 1) / R;
+  const int per_round = NQ * R;  // rows of one round of the CTA's teams
+  for (int64_t u = threadIdx.x;; u += blockDim.x) {
+    const int64_t k = u / per_round;
+    const int rem = (int)(u - k * per_round);
+    const int64_t c0 = (int64_t)blockIdx.x * NQ + k * (int64_t)gridDim.x * NQ;
+    if (c0 >= n_chunks) break;
+    const int64_t c = c0 + rem / R;
+    const int64_t row = c * R + rem % R;
+    if (c >= n_chunks || row >= p.P) continue;
+    float nrm[4];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if ((d & 3) == 0) philox_normal4(key, (uint64_t)(p.person_offset + row), (uint32_t)(d >> 2), nrm);
+      p.eps_draw[row * D + d] = nrm[d & 3];
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // One group of 4 consecutive items of one person: link, Bernoulli
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
         s_param[(size_t)(D + 1) * I + j] = 1.0f / (1.0f + expf(-p.item_feat[(size_t)j * F + D + 1]));
     }
   }
+  fused_draw_noise<D>(p, NQ);
   __syncthreads();
 
   // per-CTA results
@@ -650,22 +664,16 @@ cudaError_t launch_fused_md(const FusedParams& p, int grid, size_t smem, bool gr
 
 template <int MODEL, int D, int LPP, int NG>
 static cudaError_t launch_fused_cfg(const FusedParams& p, int grid, size_t smem, bool grad, cudaStream_t st) {
-  // opt in to > 48 KB dynamic shared memory once per kernel (and per growth)
-  static size_t smem_set[2] = {0, 0};
+  // the opt-in to > 48 KB dynamic shared memory is per device and per function: set it on every
+  // launch (a host-side attribute write, ~1 us) instead of caching it in process-wide state
   cudaError_t e;
   if (grad) {
     auto k = fused_uncond_kernel<MODEL, D, LPP, NG, true>;
-    if (smem > smem_set[1]) {
-      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      smem_set[1] = smem;
-    }
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<grid, kFusedThreads, smem, st>>>(p);
   } else {
     auto k = fused_uncond_kernel<MODEL, D, LPP, NG, false>;
-    if (smem > smem_set[0]) {
-      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-      smem_set[0] = smem;
-    }
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     k<<<grid, kFusedThreads, smem, st>>>(p);
   }
   return cudaGetLastError();

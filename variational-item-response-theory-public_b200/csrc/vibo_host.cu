@@ -71,12 +71,22 @@ int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
                          void* stream) {
   if (desc == nullptr || response_host == nullptr || mask_host == nullptr || staging == nullptr ||
       out_scalars == nullptr || chunk_person <= 0)
-    return VIBO_ERR_BAD_ARGUMENT;
+    return vibo::set_last_error(VIBO_ERR_BAD_ARGUMENT,
+                                "vibo_fused_elbo_host: desc, response_host, mask_host, staging and out_scalars "
+                                "are required and chunk_person must be > 0");
   const vibo_desc& d = *desc;
   const StagingLayout L = staging_layout(d, chunk_person);
-  if (staging_bytes < L.total) return VIBO_ERR_WORKSPACE;
+  if (staging_bytes < L.total)
+    return vibo::set_last_error(VIBO_ERR_WORKSPACE, "staging smaller than vibo_host_staging_bytes(desc, chunk_person)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g_pipe.ensure() != cudaSuccess) return VIBO_ERR_CUDA;
+  cudaError_t ce;
+#define VIBO_HOST_CUDA(call, where)                                                                  \
+  do {                                                                                               \
+    if ((ce = (call)) != cudaSuccess)                                                                \
+      return vibo::set_last_error(VIBO_ERR_CUDA, (std::string("vibo_fused_elbo_host: ") + where + ": " + \
+                                                  cudaGetErrorString(ce)).c_str());                  \
+  } while (0)
+  VIBO_HOST_CUDA(g_pipe.ensure(), "copy stream / events");
   char* base = static_cast<char*>(staging);
   double* tmp_scalars = reinterpret_cast<double*>(base + L.scalars);
   float* tmp_g_table = reinterpret_cast<float*>(base + L.g_table);
@@ -86,26 +96,28 @@ int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
   const int n_table = 2 * (d.conditional ? d.num_item : 1) * 2 * d.ability_dim;
   const int n_item = (int)(d.num_item * F);
 
-  cudaMemsetAsync(out_scalars, 0, 2 * sizeof(double), st);
+  VIBO_HOST_CUDA(cudaMemsetAsync(out_scalars, 0, 2 * sizeof(double), st), "memset");
   if (grad) {
-    cudaMemsetAsync(g_table, 0, sizeof(float) * n_table, st);
-    cudaMemsetAsync(g_item, 0, sizeof(float) * n_item, st);
+    VIBO_HOST_CUDA(cudaMemsetAsync(g_table, 0, sizeof(float) * n_table, st), "memset");
+    VIBO_HOST_CUDA(cudaMemsetAsync(g_item, 0, sizeof(float) * n_item, st), "memset");
   }
   // staging buffers may still be read by earlier work on `st`
-  cudaEventRecord(g_pipe.start, st);
-  cudaStreamWaitEvent(g_pipe.copy, g_pipe.start, 0);
+  VIBO_HOST_CUDA(cudaEventRecord(g_pipe.start, st), "event record");
+  VIBO_HOST_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.start, 0), "stream wait");
 
   int64_t c = 0;
   for (int64_t r0 = 0; r0 < d.num_person; r0 += chunk_person, ++c) {
     const int b = (int)(c & 1);
     const int64_t n = (d.num_person - r0 < chunk_person) ? d.num_person - r0 : chunk_person;
-    if (c >= 2) cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0);
-    cudaMemcpyAsync(base + L.resp[b], response_host + (size_t)r0 * d.num_item,
-                    (size_t)n * d.num_item * sizeof(float), cudaMemcpyHostToDevice, g_pipe.copy);
-    cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item, (size_t)n * d.num_item,
-                    cudaMemcpyHostToDevice, g_pipe.copy);
-    cudaEventRecord(g_pipe.copied[b], g_pipe.copy);
-    cudaStreamWaitEvent(st, g_pipe.copied[b], 0);
+    if (c >= 2) VIBO_HOST_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0), "stream wait");
+    VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.resp[b], response_host + (size_t)r0 * d.num_item,
+                                   (size_t)n * d.num_item * sizeof(float), cudaMemcpyHostToDevice, g_pipe.copy),
+                   "H2D copy of response rows");
+    VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item, (size_t)n * d.num_item,
+                                   cudaMemcpyHostToDevice, g_pipe.copy),
+                   "H2D copy of mask rows");
+    VIBO_HOST_CUDA(cudaEventRecord(g_pipe.copied[b], g_pipe.copy), "event record");
+    VIBO_HOST_CUDA(cudaStreamWaitEvent(st, g_pipe.copied[b], 0), "stream wait");
     vibo_desc dc = d;
     dc.num_person = n;
     dc.person_offset = d.person_offset + r0;
@@ -115,21 +127,21 @@ int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
                                    beta, tmp_scalars, nullptr, nullptr, nullptr,
                                    grad ? tmp_g_table : nullptr, grad ? tmp_g_item : nullptr, workspace,
                                    workspace_bytes, st);
-    if (rc != VIBO_OK) return rc;
+    if (rc != VIBO_OK) return rc;  // vibo_fused_elbo recorded the message
     if (grad) {
-      if (vibo::launch_accumulate(g_table, tmp_g_table, n_table, out_scalars, tmp_scalars, 2, st) != cudaSuccess)
-        return VIBO_ERR_CUDA;
-      if (vibo::launch_accumulate(g_item, tmp_g_item, n_item, nullptr, nullptr, 0, st) != cudaSuccess)
-        return VIBO_ERR_CUDA;
+      VIBO_HOST_CUDA(vibo::launch_accumulate(g_table, tmp_g_table, n_table, out_scalars, tmp_scalars, 2, st),
+                     "accumulate");
+      VIBO_HOST_CUDA(vibo::launch_accumulate(g_item, tmp_g_item, n_item, nullptr, nullptr, 0, st), "accumulate");
     } else {
-      if (vibo::launch_accumulate(nullptr, nullptr, 0, out_scalars, tmp_scalars, 2, st) != cudaSuccess)
-        return VIBO_ERR_CUDA;
+      VIBO_HOST_CUDA(vibo::launch_accumulate(nullptr, nullptr, 0, out_scalars, tmp_scalars, 2, st), "accumulate");
     }
-    cudaEventRecord(g_pipe.consumed[b], st);
+    VIBO_HOST_CUDA(cudaEventRecord(g_pipe.consumed[b], st), "event record");
   }
   if (out_scalars_host != nullptr)
-    cudaMemcpyAsync(out_scalars_host, out_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
-  if (cudaStreamSynchronize(st) != cudaSuccess) return VIBO_ERR_CUDA;
+    VIBO_HOST_CUDA(cudaMemcpyAsync(out_scalars_host, out_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, st),
+                   "D2H copy of the scalars");
+  VIBO_HOST_CUDA(cudaStreamSynchronize(st), "stream synchronize");
+#undef VIBO_HOST_CUDA
   return VIBO_OK;
 }
 

@@ -12,6 +12,7 @@ namespace vibo {
 int sm_count();
 void note_launch(int n = 1);  // counts kernel launches (vibo_launch_count)
 int item_width_host(int model, int D);
+int set_last_error(int code, const char* msg);  // records vibo_last_error() for this thread, returns code
 int general_max_items(int D);
 int general_grid(int64_t P, int I, int D);
 int bernoulli_grid(int64_t n);

@@ -224,6 +224,7 @@ class VIBO_1PL(nn.Module):
         self.replace_missing_with_prior = replace_missing_with_prior
         self.n_norm_flows = n_norm_flows
         self._set_item_feat_dim()
+        self._check_kernel_limits()
 
         # construction order == reference (models.py:281-329): RNG-compatible
         if conditional_posterior:
@@ -241,6 +242,22 @@ class VIBO_1PL(nn.Module):
         self.apply(self.weights_init)
 
     # ------------------------------------------------------------------ setup
+    def _check_kernel_limits(self):
+        """Fail at construction, not at the first step, when the kernels cannot take this shape."""
+        from . import _lib
+        if self.ability_dim > _lib.MAX_ABILITY_DIM:
+            raise ValueError(f"ability_dim {self.ability_dim} > {_lib.MAX_ABILITY_DIM} supported by the B200 kernels")
+        try:
+            lib = _lib.load()
+        except Exception:
+            return  # no library here (pure host-logic tests); the kernels check again at call time
+        import ctypes
+        d = _lib.Desc(0, self.num_item, self.ability_dim, self.irt_num, int(self.conditional_posterior), 0, 0, 0)
+        limit = int(lib.vibo_max_items(ctypes.byref(d)))
+        if self.num_item > limit:
+            raise ValueError(f"num_item {self.num_item} exceeds the B200 kernels' limit of {limit} items for "
+                             f"ability_dim {self.ability_dim} (item slabs are register-resident)")
+
     def _set_item_feat_dim(self):
         self.item_feat_dim = {1: 1, 2: self.latent_dim + 1, 3: self.latent_dim + 2}[self.irt_num]
 
