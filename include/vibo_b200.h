@@ -224,6 +224,41 @@ int vibo_param_backward(const vibo_desc* desc, int hidden_dim, const float* mu_l
                         float* g_w4, float* g_b4, void* stream);
 
 /*
+ * The training / evaluation step of vibo.py:243-268 (:285-312) for the UNCONDITIONAL model as a
+ * handful of launches with no host involvement between them (so the whole step is one CUDA
+ * graph): vibo_param_forward_draw -> vibo_fused_elbo_graph -> vibo_step_tail
+ * [-> vibo_comm_allreduce] -> vibo_adam_step.
+ *
+ *   vibo_param_forward_draw  vibo_param_forward with the item noise drawn in-kernel:
+ *             eps_item_out (I, F) = Philox(seed_state[0] + seed_state[1]) on the counter range
+ *             [2^62, 2^62 + I F) (== vibo_philox_normal with person_offset 2^62, ability_dim 1,
+ *             num_person I F): ONE global draw per step, identical on every rank (models.py:361).
+ *   vibo_step_tail  loss_out[0] = -LL + beta KL_theta + item_scale beta KL_item  (VIBO_ELBO_KL) or
+ *             -LL - person_term + item_scale item_term (VIBO_ELBO_SAMPLE) from out_scalars of the
+ *             fused entry and item_term of the forward; item_scale = 1 / world_size when persons
+ *             are sharded.  With the gradient pointers given it also runs vibo_param_backward
+ *             (g_item_term = item_scale * beta, resp. item_scale).  counter0 / counter1 (device
+ *             int64, may be NULL) are incremented by one: seed_state + 1 (the step) and the Adam
+ *             step count, after every kernel of the step that reads them.
+ *   vibo_adam_step  torch.optim.Adam's update (vibo.py:221; no weight decay, no amsgrad) on flat
+ *             buffers; `step` (device int64) is the 1-based index of this update.
+ */
+int vibo_param_forward_draw(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
+                            const float* logvar_lookup, const uint64_t* seed_state, const float* w0,
+                            const float* b0, const float* w2, const float* b2, const float* w4,
+                            const float* b4, float* eps_item_out, float* item_feat, float* table,
+                            float* hidden, double* item_term, void* stream);
+int vibo_step_tail(const vibo_desc* desc, int hidden_dim, float beta, float item_scale,
+                   const double* scalars, const double* item_term, float* loss_out, int64_t* counter0,
+                   int64_t* counter1, const float* mu_lookup, const float* logvar_lookup,
+                   const float* eps_item, const float* w2, const float* w4, const float* hidden,
+                   const float* g_table, const float* g_item, float* g_mu_lookup,
+                   float* g_logvar_lookup, float* g_w0, float* g_b0, float* g_w2, float* g_b2,
+                   float* g_w4, float* g_b4, void* stream);
+int vibo_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   const int64_t* step, float lr, float beta1, float beta2, float eps, void* stream);
+
+/*
  * Planar normalizing flows on the abilities (--n-norm-flows K), per person and
  * fused with the reparameterised draw and the person-side terms of the flow
  * form of the ELBO [flows.py:21-41, :58-66; models.py:342-348, :406-424]:

@@ -412,6 +412,61 @@ int vibo_param_forward(const vibo_desc* desc, int hidden_dim, const float* mu_lo
   return VIBO_OK;
 }
 
+int vibo_param_forward_draw(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
+                            const float* logvar_lookup, const uint64_t* seed_state, const float* w0,
+                            const float* b0, const float* w2, const float* b2, const float* w4,
+                            const float* b4, float* eps_item_out, float* item_feat, float* table,
+                            float* hidden, double* item_term, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (desc->conditional) return fail(VIBO_ERR_UNSUPPORTED, "vibo_param_forward_draw covers the unconditional encoder only");
+  if (hidden_dim < 1 || hidden_dim > 256) return fail(VIBO_ERR_UNSUPPORTED, "hidden_dim must be in 1..256");
+  if (!mu_lookup || !logvar_lookup || !seed_state || !w0 || !b0 || !w2 || !b2 || !w4 || !b4 || !eps_item_out ||
+      !item_feat || !table || !hidden || !item_term)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  const int F = vibo::item_width_host(desc->irt_model, desc->ability_dim);
+  VIBO_CUDA(vibo::launch_param_forward(desc->num_item, F, desc->ability_dim, hidden_dim, desc->elbo_form,
+                                       mu_lookup, logvar_lookup, nullptr, w0, b0, w2, b2, w4, b4, item_feat,
+                                       table, hidden, item_term, static_cast<cudaStream_t>(stream), seed_state,
+                                       eps_item_out),
+            "param_forward");
+  return VIBO_OK;
+}
+
+int vibo_step_tail(const vibo_desc* desc, int hidden_dim, float beta, float item_scale,
+                   const double* scalars, const double* item_term, float* loss_out, int64_t* counter0,
+                   int64_t* counter1, const float* mu_lookup, const float* logvar_lookup,
+                   const float* eps_item, const float* w2, const float* w4, const float* hidden,
+                   const float* g_table, const float* g_item, float* g_mu_lookup,
+                   float* g_logvar_lookup, float* g_w0, float* g_b0, float* g_w2, float* g_b2,
+                   float* g_w4, float* g_b4, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (desc->conditional) return fail(VIBO_ERR_UNSUPPORTED, "vibo_step_tail covers the unconditional encoder only");
+  if (hidden_dim < 1 || hidden_dim > 256) return fail(VIBO_ERR_UNSUPPORTED, "hidden_dim must be in 1..256");
+  if (!scalars || !item_term || !loss_out) return fail(VIBO_ERR_BAD_ARGUMENT, "scalars, item_term and loss_out are required");
+  const bool grad = g_mu_lookup != nullptr;
+  if (grad && (!mu_lookup || !logvar_lookup || !eps_item || !w2 || !w4 || !hidden || !g_table || !g_item ||
+               !g_logvar_lookup || !g_w0 || !g_b0 || !g_w2 || !g_b2 || !g_w4 || !g_b4))
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer (all gradient outputs and their inputs, or none)");
+  const int F = vibo::item_width_host(desc->irt_model, desc->ability_dim);
+  VIBO_CUDA(vibo::launch_step_tail(desc->num_item, F, desc->ability_dim, hidden_dim, desc->elbo_form, beta,
+                                   item_scale, scalars, item_term, loss_out, counter0, counter1, grad, mu_lookup,
+                                   logvar_lookup, eps_item, w2, w4, hidden, g_table, g_item, g_mu_lookup,
+                                   g_logvar_lookup, g_w0, g_b0, g_w2, g_b2, g_w4, g_b4,
+                                   static_cast<cudaStream_t>(stream)),
+            "step_tail");
+  return VIBO_OK;
+}
+
+int vibo_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   const int64_t* step, float lr, float beta1, float beta2, float eps, void* stream) {
+  if (n < 0 || n > 0x7fffffff) return fail(VIBO_ERR_BAD_ARGUMENT, "n out of range");
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  VIBO_CUDA(vibo::launch_adam((int)n, param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps,
+                              static_cast<cudaStream_t>(stream)),
+            "adam");
+  return VIBO_OK;
+}
+
 int vibo_param_backward(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
                         const float* logvar_lookup, const float* eps_item, const float* w2,
                         const float* w4, const float* hidden, const float* g_table,

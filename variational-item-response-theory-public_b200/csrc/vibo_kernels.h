@@ -80,7 +80,16 @@ cudaError_t launch_accumulate(float* dst, const float* src, int n, double* dst2,
 cudaError_t launch_param_forward(int I, int F, int D, int H, int form, const float* mu, const float* lv,
                                  const float* eps, const float* w0, const float* b0, const float* w2,
                                  const float* b2, const float* w4, const float* b4, float* item_feat,
-                                 float* table, float* hidden, double* item_term, cudaStream_t st);
+                                 float* table, float* hidden, double* item_term, cudaStream_t st,
+                                 const uint64_t* seed_state = nullptr, float* eps_out = nullptr);
+cudaError_t launch_step_tail(int I, int F, int D, int H, int form, float beta, float item_scale,
+                             const double* scalars, const double* item_term, float* loss_out, int64_t* counter0,
+                             int64_t* counter1, bool grad, const float* mu, const float* lv, const float* eps,
+                             const float* w2, const float* w4, const float* hidden, const float* g_table,
+                             const float* g_item, float* g_mu, float* g_lv, float* g_w0, float* g_b0,
+                             float* g_w2, float* g_b2, float* g_w4, float* g_b4, cudaStream_t st);
+cudaError_t launch_adam(int n, float* param, const float* grad, float* m, float* v, const int64_t* step, float lr,
+                        float b1, float b2, float eps, cudaStream_t st);
 cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const float* mu, const float* lv,
                                   const float* eps, const float* w2, const float* w4, const float* hidden,
                                   const float* g_table, const float* g_item, const float* g_term,

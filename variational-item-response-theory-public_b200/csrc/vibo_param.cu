@@ -19,6 +19,7 @@ namespace vibo {
 
 constexpr int kParamThreads = 256;
 constexpr int kMaxHidden = 256;
+constexpr uint64_t kItemNoiseStream = 1ull << 62;  // "person index" range of the item noise
 
 __device__ __forceinline__ float elu(float a) { return a > 0.0f ? a : expm1f(a); }
 // d ELU / d a expressed through the activation h = ELU(a): 1 for a > 0, exp(a) = h + 1 otherwise
@@ -27,6 +28,7 @@ __device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.0f ? 
 __global__ void __launch_bounds__(kParamThreads)
 param_forward_kernel(int I, int F, int D, int H, int form, const float* __restrict__ mu,
                      const float* __restrict__ lv, const float* __restrict__ eps,
+                     const uint64_t* __restrict__ seed_state, float* __restrict__ eps_out,
                      const float* __restrict__ w0, const float* __restrict__ b0,
                      const float* __restrict__ w2, const float* __restrict__ b2,
                      const float* __restrict__ w4, const float* __restrict__ b4,
@@ -58,8 +60,21 @@ param_forward_kernel(int I, int F, int D, int H, int form, const float* __restri
     return;
   }
   double acc = 0.0;
+  const uint64_t key = seed_state != nullptr ? seed_state[0] + seed_state[1] : 0;
   for (int k = t; k < I * F; k += blockDim.x) {
-    const float m = mu[k], l = lv[k], e = eps[k];
+    const float m = mu[k], l = lv[k];
+    float e;
+    if (eps != nullptr) {
+      e = eps[k];
+    } else {
+      // ONE global item draw per step (models.py:361), identical on every rank: Philox(seed + step)
+      // on a counter range disjoint from the persons' (same stream as vibo_philox_normal with
+      // person_offset = kItemNoiseStream, ability_dim = 1)
+      float nrm[4];
+      philox_normal4(key, kItemNoiseStream + (uint64_t)k, 0u, nrm);
+      e = nrm[0];
+      eps_out[k] = e;
+    }
     const float d = fmaf(e, expf(0.5f * l), m);
     item_feat[k] = d;
     if (form == VIBO_ELBO_KL) acc += (double)(-0.5f * (1.0f + l - m * m - expf(l)));
@@ -75,15 +90,15 @@ param_forward_kernel(int I, int F, int D, int H, int form, const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(kParamThreads)
-param_backward_kernel(int I, int F, int D, int H, int form, const float* __restrict__ mu,
-                      const float* __restrict__ lv, const float* __restrict__ eps,
-                      const float* __restrict__ w2, const float* __restrict__ w4,
-                      const float* __restrict__ hidden, const float* __restrict__ g_table,
-                      const float* __restrict__ g_item, const float* __restrict__ g_term_ptr,
-                      float* __restrict__ g_mu, float* __restrict__ g_lv, float* __restrict__ g_w0,
-                      float* __restrict__ g_b0, float* __restrict__ g_w2, float* __restrict__ g_b2,
-                      float* __restrict__ g_w4, float* __restrict__ g_b4) {
+__device__ __forceinline__ void
+param_backward_body(int I, int F, int D, int H, int form, const float* __restrict__ mu,
+                    const float* __restrict__ lv, const float* __restrict__ eps,
+                    const float* __restrict__ w2, const float* __restrict__ w4,
+                    const float* __restrict__ hidden, const float* __restrict__ g_table,
+                    const float* __restrict__ g_item, const float gt,
+                    float* __restrict__ g_mu, float* __restrict__ g_lv, float* __restrict__ g_w0,
+                    float* __restrict__ g_b0, float* __restrict__ g_w2, float* __restrict__ g_b2,
+                    float* __restrict__ g_w4, float* __restrict__ g_b4) {
   __shared__ float s_h[2][2][kMaxHidden];   // activations h1, h2
   __shared__ float s_ga[2][2][kMaxHidden];  // gradients w.r.t. pre-activations a1, a2
   __shared__ float s_go[2][2 * VIBO_MAX_ABILITY_DIM];
@@ -125,7 +140,7 @@ param_backward_kernel(int I, int F, int D, int H, int form, const float* __restr
     }
     return;
   }
-  const float gt = *g_term_ptr;  // d loss / d item_term
+  // gt = d loss / d item_term
   for (int k = t; k < I * F; k += blockDim.x) {
     const float m = mu[k], l = lv[k], e = eps[k];
     const float sd = expf(0.5f * l);
@@ -144,13 +159,83 @@ param_backward_kernel(int I, int F, int D, int H, int form, const float* __restr
   }
 }
 
+__global__ void __launch_bounds__(kParamThreads)
+param_backward_kernel(int I, int F, int D, int H, int form, const float* __restrict__ mu,
+                      const float* __restrict__ lv, const float* __restrict__ eps,
+                      const float* __restrict__ w2, const float* __restrict__ w4,
+                      const float* __restrict__ hidden, const float* __restrict__ g_table,
+                      const float* __restrict__ g_item, const float* __restrict__ g_term_ptr,
+                      float* __restrict__ g_mu, float* __restrict__ g_lv, float* __restrict__ g_w0,
+                      float* __restrict__ g_b0, float* __restrict__ g_w2, float* __restrict__ g_b2,
+                      float* __restrict__ g_w4, float* __restrict__ g_b4) {
+  param_backward_body(I, F, D, H, form, mu, lv, eps, w2, w4, hidden, g_table, g_item, *g_term_ptr, g_mu, g_lv,
+                      g_w0, g_b0, g_w2, g_b2, g_w4, g_b4);
+}
+
+// Tail of a fused step (vibo_step_tail): loss assembly, the parameter chain rule, and the step
+// counters, in ONE launch:
+//   loss = -LL + beta KL_theta + item_scale beta KL_item            (VIBO_ELBO_KL,  models.py:428-430)
+//   loss = -LL - person_term + item_scale item_term                 (VIBO_ELBO_SAMPLE, :433-441)
+// (item_scale = 1 / world_size in a person-sharded run), written to out[0]; the gradients of
+// every parameter go to the caller's pointers (normally views of out[1:], the flat buffer the
+// all-reduce and Adam work on).  counters[0..n) are incremented by one by block 0 AFTER the
+// kernels that read them in this step (stream order): {seed, step}[1], the Adam step count.
+__global__ void __launch_bounds__(kParamThreads)
+step_tail_kernel(int I, int F, int D, int H, int form, float beta, float item_scale,
+                 const double* __restrict__ scalars, const double* __restrict__ item_term,
+                 float* __restrict__ loss_out, int64_t* counter0, int64_t* counter1, bool grad,
+                 const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
+                 const float* __restrict__ w2, const float* __restrict__ w4,
+                 const float* __restrict__ hidden, const float* __restrict__ g_table,
+                 const float* __restrict__ g_item, float* __restrict__ g_mu, float* __restrict__ g_lv,
+                 float* __restrict__ g_w0, float* __restrict__ g_b0, float* __restrict__ g_w2,
+                 float* __restrict__ g_b2, float* __restrict__ g_w4, float* __restrict__ g_b4) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double ll = scalars[0], term = scalars[1], it = *item_term;
+    const double loss = form == VIBO_ELBO_KL ? -ll + (double)beta * term + (double)item_scale * (double)beta * it
+                                             : -ll - term + (double)item_scale * it;
+    *loss_out = (float)loss;
+    if (counter0 != nullptr) *counter0 += 1;
+    if (counter1 != nullptr) *counter1 += 1;
+  }
+  if (!grad) return;
+  const float gt = form == VIBO_ELBO_KL ? item_scale * beta : item_scale;
+  param_backward_body(I, F, D, H, form, mu, lv, eps, w2, w4, hidden, g_table, g_item, gt, g_mu, g_lv, g_w0, g_b0,
+                      g_w2, g_b2, g_w4, g_b4);
+}
+
+// torch.optim.Adam (vibo.py:221: defaults betas (0.9, 0.999), eps 1e-8, no weight decay, no
+// amsgrad) over flat buffers; `step` is the 1-based count of THIS update, read from device memory
+// (incremented by step_tail_kernel), so the launch is identical on every CUDA-graph replay.
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2
+//   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(int n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+            float* __restrict__ v, const int64_t* __restrict__ step, float lr, float b1, float b2, float eps) {
+  const double t = (double)*step;
+  const float bc1 = (float)(1.0 - pow((double)b1, t));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const float step_size = lr / bc1;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const float g = grad[k];
+    const float mk = fmaf(b1, m[k], (1.0f - b1) * g);
+    const float vk = fmaf(b2, v[k], (1.0f - b2) * g * g);
+    m[k] = mk;
+    v[k] = vk;
+    const float denom = sqrtf(vk) / bc2_sqrt + eps;
+    param[k] -= step_size * (mk / denom);
+  }
+}
+
 cudaError_t launch_param_forward(int I, int F, int D, int H, int form, const float* mu, const float* lv,
                                  const float* eps, const float* w0, const float* b0, const float* w2,
                                  const float* b2, const float* w4, const float* b4, float* item_feat,
-                                 float* table, float* hidden, double* item_term, cudaStream_t st) {
+                                 float* table, float* hidden, double* item_term, cudaStream_t st,
+                                 const uint64_t* seed_state, float* eps_out) {
   if (H > kMaxHidden) return cudaErrorInvalidValue;
-  param_forward_kernel<<<2, kParamThreads, 0, st>>>(I, F, D, H, form, mu, lv, eps, w0, b0, w2, b2, w4, b4,
-                                                    item_feat, table, hidden, item_term);
+  if (eps == nullptr && (seed_state == nullptr || eps_out == nullptr)) return cudaErrorInvalidValue;
+  param_forward_kernel<<<2, kParamThreads, 0, st>>>(I, F, D, H, form, mu, lv, eps, seed_state, eps_out, w0, b0,
+                                                    w2, b2, w4, b4, item_feat, table, hidden, item_term);
   note_launch();
   return cudaGetLastError();
 }
@@ -164,6 +249,31 @@ cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const fl
   param_backward_kernel<<<2, kParamThreads, 0, st>>>(I, F, D, H, form, mu, lv, eps, w2, w4, hidden,
                                                      g_table, g_item, g_term, g_mu, g_lv, g_w0, g_b0, g_w2,
                                                      g_b2, g_w4, g_b4);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_step_tail(int I, int F, int D, int H, int form, float beta, float item_scale,
+                             const double* scalars, const double* item_term, float* loss_out, int64_t* counter0,
+                             int64_t* counter1, bool grad, const float* mu, const float* lv, const float* eps,
+                             const float* w2, const float* w4, const float* hidden, const float* g_table,
+                             const float* g_item, float* g_mu, float* g_lv, float* g_w0, float* g_b0,
+                             float* g_w2, float* g_b2, float* g_w4, float* g_b4, cudaStream_t st) {
+  if (H > kMaxHidden) return cudaErrorInvalidValue;
+  step_tail_kernel<<<grad ? 2 : 1, kParamThreads, 0, st>>>(I, F, D, H, form, beta, item_scale, scalars, item_term,
+                                                            loss_out, counter0, counter1, grad, mu, lv, eps, w2,
+                                                            w4, hidden, g_table, g_item, g_mu, g_lv, g_w0, g_b0,
+                                                            g_w2, g_b2, g_w4, g_b4);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam(int n, float* param, const float* grad, float* m, float* v, const int64_t* step, float lr,
+                        float b1, float b2, float eps, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  int blocks = (n + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  adam_kernel<<<blocks, 256, 0, st>>>(n, param, grad, m, v, step, lr, b1, b2, eps);
   note_launch();
   return cudaGetLastError();
 }

@@ -33,14 +33,135 @@ def shard_bounds(num_person: int, rank: int, world_size: int):
     return start, start + base + (1 if rank < rem else 0)
 
 
+class FusedStep:
+    """The step of the UNCONDITIONAL product-of-experts model without flows as five launches of
+    libvibo_b200.so and nothing else (no autograd, no torch kernels):
+
+        vibo_param_forward[_draw] -> vibo_fused_elbo[_graph] (+ finalize) -> vibo_step_tail
+        [-> all-reduce] -> vibo_adam_step
+
+    Parameters, gradients and Adam moments live in flat buffers; the module's parameters are
+    re-homed as views of ``theta`` (state_dict / load_state_dict keep working), ``p.grad`` are
+    views of ``flat[1:]``.  Mirrors reference vibo.py:243-268 (train) / :285-312 (test)."""
+
+    def __init__(self, trainer):
+        import ctypes as C
+        from . import _lib, kernels as K
+        self.C, self.K, self.lib = C, K, _lib.load()
+        self._check = _lib.check
+        t = self.t = trainer
+        m = t.model
+        dev = t.flat.device
+        mlp = m.ability_encoder.mlp
+        want = [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, mlp[4].weight, mlp[4].bias,
+                m.item_encoder.mu_lookup.weight, m.item_encoder.logvar_lookup.weight]
+        assert len(t.params) == len(want) and all(a is b for a, b in zip(t.params, want)), \
+            "unexpected parameter order"
+        n = t.flat.numel() - 1
+        self.n = n
+        self.theta = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in t.params:
+                k = p.numel()
+                self.theta[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.theta[off:off + k].view_as(p)
+                off += k
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.adam_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        I, F, D, H = m.num_item, m.item_feat_dim, m.ability_dim, m.hidden_dim
+        self.I, self.F, self.D, self.H = I, F, D, H
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.eps_item = torch.empty(I, F, **f32)
+        self.item_feat = torch.empty(I, F, **f32)
+        self.table = torch.empty(2, 1, 2 * D, **f32)
+        self.hidden = torch.empty(2, 2, H, **f32)
+        self.item_term = torch.empty(1, dtype=torch.float64, device=dev)
+        self.scalars = torch.empty(2, dtype=torch.float64, device=dev)
+        self.g_table = torch.empty(2, 1, 2 * D, **f32)
+        self.g_item = torch.empty(I, F, **f32)
+        self.lr = float(trainer.lr)
+
+    @staticmethod
+    def eligible(trainer, response):
+        m = trainer.model
+        return (trainer.on_gpu and response.is_cuda and m.ability_merge == 'product'
+                and not m.conditional_posterior and m.n_norm_flows == 0 and m.hidden_dim <= 256
+                and getattr(m, "fuse_param_chain", True))
+
+    def run(self, response, mask, train, eps_item=None, eps_ability=None):
+        from . import functional as VF
+        C, K, lib, t, m = self.C, self.K, self.lib, self.t, self.t.model
+        resp, msk = VF.prepare_rows(response, mask)
+        K._check_rows(resp, msk)
+        P = resp.shape[0]
+        dev = resp.device
+        form = K.ELBO_KL if t.use_kl else K.ELBO_SAMPLE
+        desc = K.make_desc(P, self.I, self.D, m.irt_num, False, m.ability_encoder.missing_policy, form,
+                           t.person_offset)
+        st = K._stream(dev)
+        ptr = K._ptr
+        mu, lv = t.params[6], t.params[7]
+        w0, b0, w2, b2, w4, b4 = t.params[:6]
+        seed = t.seed_state
+        if eps_item is None:
+            self._check(lib.vibo_param_forward_draw(C.byref(desc), self.H, ptr(mu), ptr(lv), ptr(seed), ptr(w0),
+                                                    ptr(b0), ptr(w2), ptr(b2), ptr(w4), ptr(b4),
+                                                    ptr(self.eps_item), ptr(self.item_feat), ptr(self.table),
+                                                    ptr(self.hidden), ptr(self.item_term), st),
+                        "vibo_param_forward_draw")
+            e_i = self.eps_item
+        else:
+            e_i = eps_item.contiguous()
+            self._check(lib.vibo_param_forward(C.byref(desc), self.H, ptr(mu), ptr(lv), ptr(e_i), ptr(w0), ptr(b0),
+                                               ptr(w2), ptr(b2), ptr(w4), ptr(b4), ptr(self.item_feat),
+                                               ptr(self.table), ptr(self.hidden), ptr(self.item_term), st),
+                        "vibo_param_forward")
+        ws = K.workspace(desc, dev)
+        gt, gi = (ptr(self.g_table), ptr(self.g_item)) if train else (None, None)
+        if eps_ability is None:
+            self._check(lib.vibo_fused_elbo_graph(C.byref(desc), ptr(resp), ptr(msk), ptr(self.table),
+                                                  ptr(self.item_feat), ptr(seed), C.c_float(t.beta),
+                                                  ptr(self.scalars), None, None, None, gt, gi, ptr(ws),
+                                                  ws.numel(), st), "vibo_fused_elbo_graph")
+        else:
+            self._check(lib.vibo_fused_elbo(C.byref(desc), ptr(resp), ptr(msk), ptr(self.table),
+                                            ptr(self.item_feat), ptr(eps_ability.contiguous()), C.c_uint64(0),
+                                            C.c_float(t.beta), ptr(self.scalars), None, None, None, gt, gi,
+                                            ptr(ws), ws.numel(), st), "vibo_fused_elbo")
+        flat = t.flat
+        step_ptr = C.c_void_p(seed.data_ptr() + 8)  # seed_state[1]
+        if train:
+            g = [C.c_void_p(p.grad.data_ptr()) for p in t.params]
+            grads = [g[6], g[7], g[0], g[1], g[2], g[3], g[4], g[5]]
+        else:
+            grads = [None] * 8
+        self._check(lib.vibo_step_tail(C.byref(desc), self.H, C.c_float(t.beta), C.c_float(1.0 / t.world_size),
+                                       ptr(self.scalars), ptr(self.item_term), ptr(flat), step_ptr,
+                                       ptr(self.adam_step) if train else None, ptr(mu), ptr(lv), ptr(e_i),
+                                       ptr(w2), ptr(w4), ptr(self.hidden), ptr(self.g_table), ptr(self.g_item),
+                                       *grads, st), "vibo_step_tail")
+        t._reduce(flat if train else flat[0:1])
+        if train:
+            self._check(lib.vibo_adam_step(self.n, ptr(self.theta), C.c_void_p(flat.data_ptr() + 4),
+                                           ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.adam_step),
+                                           C.c_float(self.lr), C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8),
+                                           st), "vibo_adam_step")
+
+
 class ShardedElboTrainer:
     """One training / evaluation step of a drop-in VIBO module over this
     rank's rows: fused ELBO forward+backward, one all-reduce, Adam
     (reference vibo.py:243-268 with the whole resident shard as the batch)."""
 
     def __init__(self, model, lr=5e-3, world_size=1, rank=0, person_offset=0, beta=1.0,
-                 use_kl_divergence=True, group=None, cuda_graph=False, seed=1234, allreduce="auto"):
+                 use_kl_divergence=True, group=None, cuda_graph=False, seed=1234, allreduce="auto",
+                 fused_step=True):
         self.model = model
+        self.lr = lr
+        self.want_fused_step = bool(fused_step)
+        self.fused = None
         self.world_size = world_size
         self.rank = rank
         self.person_offset = int(person_offset)
@@ -76,6 +197,7 @@ class ShardedElboTrainer:
                     raise
                 import warnings
                 warnings.warn("peer-memory all-reduce unavailable; using torch.distributed all_reduce")
+        self.step_taken_generic = False  # a generic (torch.optim) train step ran: stay on that path
         self._graphs = {}
         self._inject = {}
         self.graph_replays = 0
@@ -119,6 +241,24 @@ class ShardedElboTrainer:
         else:
             dist.all_reduce(buf, group=self.group)
 
+    def _use_fused(self, response):
+        """The five-launch C-ABI step where it applies (decided on first use, then kept: the
+        parameters move into its flat buffer)."""
+        if self.world_size > 1 and self.peer is None and self.cuda_graph:
+            return False  # torch.distributed exchange: graph(pre) -> all_reduce -> graph(Adam) form
+        if self.fused is None and self.want_fused_step and self.step_taken_generic is False \
+                and FusedStep.eligible(self, response):
+            self.fused = FusedStep(self)
+        return self.fused is not None and response.is_cuda
+
+    def adam_steps(self):
+        """Number of Adam updates applied so far (device-side count)."""
+        if self.fused is not None:
+            return int(self.fused.adam_step.item())
+        steps = {int(st["step"].item()) if torch.is_tensor(st["step"]) else int(st["step"])
+                 for st in self.opt.state.values()}
+        return max(steps) if steps else 0
+
     def _train_pre(self, response, mask, seed, eps_item=None, eps_ability=None):
         self.flat.zero_()
         loss = self._loss(response, mask, seed, eps_item, eps_ability)
@@ -131,6 +271,9 @@ class ShardedElboTrainer:
             self.seed_state[1] += 1
 
     def _train_body(self, response, mask, seed, eps_item=None, eps_ability=None):
+        if self._use_fused(response):
+            return self.fused.run(response, mask, True, eps_item, eps_ability)
+        self.step_taken_generic = True
         self._train_pre(response, mask, seed, eps_item, eps_ability)
         self._reduce(self.flat)
         self._train_post()
@@ -141,6 +284,8 @@ class ShardedElboTrainer:
             self.flat[0:1].copy_(loss.reshape(1))
 
     def _eval_body(self, response, mask, seed, eps_item=None, eps_ability=None):
+        if self._use_fused(response):
+            return self.fused.run(response, mask, False, eps_item, eps_ability)
         self._eval_pre(response, mask, seed, eps_item, eps_ability)
         self._reduce(self.flat[0:1])
         if self.seed_state is not None:
@@ -150,13 +295,23 @@ class ShardedElboTrainer:
     def _snapshot(self):
         state = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
                  for p, st in self.opt.state.items()}
-        return ([p.detach().clone() for p in self.params], state, self.seed_state.clone(), self.flat.clone())
+        fused = None
+        if self.fused is not None:
+            f = self.fused
+            fused = (f.exp_avg.clone(), f.exp_avg_sq.clone(), f.adam_step.clone())
+        return ([p.detach().clone() for p in self.params], state, self.seed_state.clone(), self.flat.clone(), fused)
 
     def _restore(self, snap):
         """Undo the eager warm-up runs that precede a capture: parameters, Adam moments and step
         counters (a freshly created state is all zeros), {seed, step}, and the flat buffer -- IN
         PLACE, so the tensors the graph captures are the ones the optimizer keeps using."""
-        params, state, seed_state, flat = snap
+        params, state, seed_state, flat, fused = snap
+        if self.fused is not None:
+            f = self.fused
+            if fused is None:   # the fused step was created during the warm-up: fresh Adam state
+                f.exp_avg.zero_(); f.exp_avg_sq.zero_(); f.adam_step.zero_()
+            else:
+                f.exp_avg.copy_(fused[0]); f.exp_avg_sq.copy_(fused[1]); f.adam_step.copy_(fused[2])
         with torch.no_grad():
             for p, saved in zip(self.params, params):
                 p.copy_(saved)
