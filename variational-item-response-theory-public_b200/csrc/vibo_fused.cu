@@ -82,7 +82,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 // Block = 32 outputs x 8 partial-slices: each thread sums every 8th partial
 // (short dependent chains), then the 8 slices are combined through shared
 // memory in a fixed order, so the result is deterministic.
-constexpr int kFinSlices = 8;
+constexpr int kFinSlices = 32;
 __global__ void __launch_bounds__(32 * kFinSlices)
 fused_finalize_kernel(int nparts, int I, int F, int DA, int D, bool grad, bool accumulate,
                       const double* __restrict__ part_scalar, const float* __restrict__ part_table,

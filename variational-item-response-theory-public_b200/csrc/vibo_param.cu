@@ -21,6 +21,27 @@ constexpr int kParamThreads = 256;
 constexpr int kMaxHidden = 256;
 constexpr uint64_t kItemNoiseStream = 1ull << 62;  // "person index" range of the item noise
 
+// Copy a row-major (rows, cols) matrix into shared memory with row pitch `ld`: every thread first
+// issues up to 16 INDEPENDENT coalesced loads, then stores them, so a 64 x 64 matrix costs one
+// global-memory latency instead of sixteen dependent ones.
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int rows, int cols, int ld) {
+  constexpr int B = 16;
+  const int n = rows * cols, nt = blockDim.x;
+  for (int k0 = threadIdx.x; k0 < n; k0 += nt * B) {
+    float v[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int k = k0 + u * nt;
+      v[u] = k < n ? src[k] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const int k = k0 + u * nt;
+      if (k < n) dst[(k / cols) * ld + (k % cols)] = v[u];
+    }
+  }
+}
+
 __device__ __forceinline__ float elu(float a) { return a > 0.0f ? a : expm1f(a); }
 // d ELU / d a expressed through the activation h = ELU(a): 1 for a > 0, exp(a) = h + 1 otherwise
 __device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.0f ? 1.0f : h + 1.0f; }
@@ -33,11 +54,25 @@ param_forward_kernel(int I, int F, int D, int H, int form, const float* __restri
                      const float* __restrict__ w2, const float* __restrict__ b2,
                      const float* __restrict__ w4, const float* __restrict__ b4,
                      float* __restrict__ item_feat, float* __restrict__ table,
-                     float* __restrict__ hidden /*[2 layers][2 rows][H]*/, double* __restrict__ item_term) {
+                     float* __restrict__ hidden /*[2 layers][2 rows][H]*/, double* __restrict__ item_term,
+                     bool staged) {
   __shared__ float s_h[2][2][kMaxHidden];
   __shared__ double s_red[kParamThreads / 32];
   const int t = threadIdx.x;
   if (blockIdx.x == 0) {
+    // The H x H and 2D x H weights are staged into shared memory with ONE round of independent,
+    // coalesced loads per thread (rows padded to H + 1 words: conflict-free both row- and
+    // column-wise); dot products then run at shared-memory latency instead of one dependent
+    // global load per term.  `staged` is false only for hidden sizes that do not fit.
+    extern __shared__ float s_w[];
+    const int ld = staged ? H + 1 : H;
+    float* s_w4 = s_w + (size_t)H * (H + 1);
+    if (staged) {
+      stage_rows(s_w, w2, H, H, ld);
+      stage_rows(s_w4, w4, 2 * D, H, ld);
+    }
+    const float* W2 = staged ? s_w : w2;
+    const float* W4 = staged ? s_w4 : w4;
     for (int k = t; k < 2 * H; k += blockDim.x) {
       const int r = k / H, h = k % H;
       s_h[0][r][h] = elu(fmaf(w0[h], (float)r, b0[h]));  // cell input is r itself: 0 or 1
@@ -46,14 +81,14 @@ param_forward_kernel(int I, int F, int D, int H, int form, const float* __restri
     for (int k = t; k < 2 * H; k += blockDim.x) {
       const int r = k / H, h = k % H;
       float a = b2[h];
-      for (int j = 0; j < H; ++j) a = fmaf(w2[(size_t)h * H + j], s_h[0][r][j], a);
+      for (int j = 0; j < H; ++j) a = fmaf(W2[(size_t)h * ld + j], s_h[0][r][j], a);
       s_h[1][r][h] = elu(a);
     }
     __syncthreads();
     for (int k = t; k < 2 * 2 * D; k += blockDim.x) {
       const int r = k / (2 * D), o = k % (2 * D);
       float a = b4[o];
-      for (int j = 0; j < H; ++j) a = fmaf(w4[(size_t)o * H + j], s_h[1][r][j], a);
+      for (int j = 0; j < H; ++j) a = fmaf(W4[(size_t)o * ld + j], s_h[1][r][j], a);
       table[r * 2 * D + o] = a;
     }
     for (int k = t; k < 2 * 2 * H; k += blockDim.x) hidden[k] = (&s_h[0][0][0])[(k / H) * kMaxHidden + (k % H)];
@@ -98,12 +133,21 @@ param_backward_body(int I, int F, int D, int H, int form, const float* __restric
                     const float* __restrict__ g_item, const float gt,
                     float* __restrict__ g_mu, float* __restrict__ g_lv, float* __restrict__ g_w0,
                     float* __restrict__ g_b0, float* __restrict__ g_w2, float* __restrict__ g_b2,
-                    float* __restrict__ g_w4, float* __restrict__ g_b4) {
+                    float* __restrict__ g_w4, float* __restrict__ g_b4, bool staged) {
   __shared__ float s_h[2][2][kMaxHidden];   // activations h1, h2
   __shared__ float s_ga[2][2][kMaxHidden];  // gradients w.r.t. pre-activations a1, a2
   __shared__ float s_go[2][2 * VIBO_MAX_ABILITY_DIM];
   const int t = threadIdx.x;
   if (blockIdx.x == 0) {
+    extern __shared__ float s_w[];  // staged w2 [H][H+1] | w4 [2D][H+1] (see param_forward_kernel)
+    const int ld = staged ? H + 1 : H;
+    float* s_w4 = s_w + (size_t)H * (H + 1);
+    if (staged) {
+      stage_rows(s_w, w2, H, H, ld);
+      stage_rows(s_w4, w4, 2 * D, H, ld);
+    }
+    const float* W2 = staged ? s_w : w2;
+    const float* W4 = staged ? s_w4 : w4;
     for (int k = t; k < 2 * 2 * H; k += blockDim.x) (&s_h[0][0][0])[(k / H) * kMaxHidden + (k % H)] = hidden[k];
     for (int k = t; k < 2 * 2 * D; k += blockDim.x) s_go[k / (2 * D)][k % (2 * D)] = g_table[k];
     __syncthreads();
@@ -116,7 +160,7 @@ param_backward_body(int I, int F, int D, int H, int form, const float* __restric
     for (int k = t; k < 2 * H; k += blockDim.x) {
       const int r = k / H, j = k % H;
       float g = 0.0f;
-      for (int o = 0; o < 2 * D; ++o) g = fmaf(w4[(size_t)o * H + j], s_go[r][o], g);
+      for (int o = 0; o < 2 * D; ++o) g = fmaf(W4[(size_t)o * ld + j], s_go[r][o], g);
       s_ga[1][r][j] = g * elu_grad_from_out(s_h[1][r][j]);
     }
     __syncthreads();
@@ -129,7 +173,7 @@ param_backward_body(int I, int F, int D, int H, int form, const float* __restric
     for (int k = t; k < 2 * H; k += blockDim.x) {
       const int r = k / H, j = k % H;
       float g = 0.0f;
-      for (int h = 0; h < H; ++h) g = fmaf(w2[(size_t)h * H + j], s_ga[1][r][h], g);
+      for (int h = 0; h < H; ++h) g = fmaf(W2[(size_t)h * ld + j], s_ga[1][r][h], g);
       s_ga[0][r][j] = g * elu_grad_from_out(s_h[0][r][j]);
     }
     __syncthreads();
@@ -167,9 +211,9 @@ param_backward_kernel(int I, int F, int D, int H, int form, const float* __restr
                       const float* __restrict__ g_item, const float* __restrict__ g_term_ptr,
                       float* __restrict__ g_mu, float* __restrict__ g_lv, float* __restrict__ g_w0,
                       float* __restrict__ g_b0, float* __restrict__ g_w2, float* __restrict__ g_b2,
-                      float* __restrict__ g_w4, float* __restrict__ g_b4) {
+                      float* __restrict__ g_w4, float* __restrict__ g_b4, bool staged) {
   param_backward_body(I, F, D, H, form, mu, lv, eps, w2, w4, hidden, g_table, g_item, *g_term_ptr, g_mu, g_lv,
-                      g_w0, g_b0, g_w2, g_b2, g_w4, g_b4);
+                      g_w0, g_b0, g_w2, g_b2, g_w4, g_b4, staged);
 }
 
 // Tail of a fused step (vibo_step_tail): loss assembly, the parameter chain rule, and the step
@@ -189,7 +233,7 @@ step_tail_kernel(int I, int F, int D, int H, int form, float beta, float item_sc
                  const float* __restrict__ hidden, const float* __restrict__ g_table,
                  const float* __restrict__ g_item, float* __restrict__ g_mu, float* __restrict__ g_lv,
                  float* __restrict__ g_w0, float* __restrict__ g_b0, float* __restrict__ g_w2,
-                 float* __restrict__ g_b2, float* __restrict__ g_w4, float* __restrict__ g_b4) {
+                 float* __restrict__ g_b2, float* __restrict__ g_w4, float* __restrict__ g_b4, bool staged) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double ll = scalars[0], term = scalars[1], it = *item_term;
     const double loss = form == VIBO_ELBO_KL ? -ll + (double)beta * term + (double)item_scale * (double)beta * it
@@ -201,7 +245,7 @@ step_tail_kernel(int I, int F, int D, int H, int form, float beta, float item_sc
   if (!grad) return;
   const float gt = form == VIBO_ELBO_KL ? item_scale * beta : item_scale;
   param_backward_body(I, F, D, H, form, mu, lv, eps, w2, w4, hidden, g_table, g_item, gt, g_mu, g_lv, g_w0, g_b0,
-                      g_w2, g_b2, g_w4, g_b4);
+                      g_w2, g_b2, g_w4, g_b4, staged);
 }
 
 // torch.optim.Adam (vibo.py:221: defaults betas (0.9, 0.999), eps 1e-8, no weight decay, no
@@ -212,9 +256,14 @@ step_tail_kernel(int I, int F, int D, int H, int form, float beta, float item_sc
 __global__ void __launch_bounds__(256)
 adam_kernel(int n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
             float* __restrict__ v, const int64_t* __restrict__ step, float lr, float b1, float b2, float eps) {
-  const double t = (double)*step;
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)*step;
+    s_bc[0] = (float)(1.0 - pow((double)b1, t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
   const float step_size = lr / bc1;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const float g = grad[k];
@@ -227,6 +276,17 @@ adam_kernel(int n, float* __restrict__ param, const float* __restrict__ grad, fl
   }
 }
 
+// Dynamic shared memory of the staged weights; 0 (not staged) when they do not fit.
+static size_t staged_bytes(int H, int D) {
+  const size_t b = ((size_t)H * (H + 1) + (size_t)2 * D * (H + 1)) * sizeof(float);
+  return b <= 160 * 1024 ? b : 0;
+}
+template <typename K>
+static cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 cudaError_t launch_param_forward(int I, int F, int D, int H, int form, const float* mu, const float* lv,
                                  const float* eps, const float* w0, const float* b0, const float* w2,
                                  const float* b2, const float* w4, const float* b4, float* item_feat,
@@ -234,8 +294,11 @@ cudaError_t launch_param_forward(int I, int F, int D, int H, int form, const flo
                                  const uint64_t* seed_state, float* eps_out) {
   if (H > kMaxHidden) return cudaErrorInvalidValue;
   if (eps == nullptr && (seed_state == nullptr || eps_out == nullptr)) return cudaErrorInvalidValue;
-  param_forward_kernel<<<2, kParamThreads, 0, st>>>(I, F, D, H, form, mu, lv, eps, seed_state, eps_out, w0, b0,
-                                                    w2, b2, w4, b4, item_feat, table, hidden, item_term);
+  const size_t sb = staged_bytes(H, D);
+  cudaError_t e0 = opt_in_smem(param_forward_kernel, sb);
+  if (e0 != cudaSuccess) return e0;
+  param_forward_kernel<<<2, kParamThreads, sb, st>>>(I, F, D, H, form, mu, lv, eps, seed_state, eps_out, w0, b0,
+                                                     w2, b2, w4, b4, item_feat, table, hidden, item_term, sb > 0);
   note_launch();
   return cudaGetLastError();
 }
@@ -246,9 +309,12 @@ cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const fl
                                   const float* g_term, float* g_mu, float* g_lv, float* g_w0, float* g_b0,
                                   float* g_w2, float* g_b2, float* g_w4, float* g_b4, cudaStream_t st) {
   if (H > kMaxHidden) return cudaErrorInvalidValue;
-  param_backward_kernel<<<2, kParamThreads, 0, st>>>(I, F, D, H, form, mu, lv, eps, w2, w4, hidden,
-                                                     g_table, g_item, g_term, g_mu, g_lv, g_w0, g_b0, g_w2,
-                                                     g_b2, g_w4, g_b4);
+  const size_t sb = staged_bytes(H, D);
+  cudaError_t e0 = opt_in_smem(param_backward_kernel, sb);
+  if (e0 != cudaSuccess) return e0;
+  param_backward_kernel<<<2, kParamThreads, sb, st>>>(I, F, D, H, form, mu, lv, eps, w2, w4, hidden,
+                                                      g_table, g_item, g_term, g_mu, g_lv, g_w0, g_b0, g_w2,
+                                                      g_b2, g_w4, g_b4, sb > 0);
   note_launch();
   return cudaGetLastError();
 }
@@ -260,10 +326,13 @@ cudaError_t launch_step_tail(int I, int F, int D, int H, int form, float beta, f
                              const float* g_item, float* g_mu, float* g_lv, float* g_w0, float* g_b0,
                              float* g_w2, float* g_b2, float* g_w4, float* g_b4, cudaStream_t st) {
   if (H > kMaxHidden) return cudaErrorInvalidValue;
-  step_tail_kernel<<<grad ? 2 : 1, kParamThreads, 0, st>>>(I, F, D, H, form, beta, item_scale, scalars, item_term,
-                                                            loss_out, counter0, counter1, grad, mu, lv, eps, w2,
-                                                            w4, hidden, g_table, g_item, g_mu, g_lv, g_w0, g_b0,
-                                                            g_w2, g_b2, g_w4, g_b4);
+  const size_t sb = grad ? staged_bytes(H, D) : 0;
+  cudaError_t e0 = opt_in_smem(step_tail_kernel, sb);
+  if (e0 != cudaSuccess) return e0;
+  step_tail_kernel<<<grad ? 2 : 1, kParamThreads, sb, st>>>(I, F, D, H, form, beta, item_scale, scalars, item_term,
+                                                             loss_out, counter0, counter1, grad, mu, lv, eps, w2,
+                                                             w4, hidden, g_table, g_item, g_mu, g_lv, g_w0, g_b0,
+                                                             g_w2, g_b2, g_w4, g_b4, sb > 0);
   note_launch();
   return cudaGetLastError();
 }
