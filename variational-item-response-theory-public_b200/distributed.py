@@ -404,7 +404,8 @@ class ShardedElboTrainer:
         seed = None if injected else self.seed_state
         if self.cuda_graph and not force_eager:
             e_i, e_a, injected = self._static_eps(response, eps_item, eps_ability)
-            key = (response.data_ptr(), mask.data_ptr(), tuple(response.shape), injected)
+            key = (response.data_ptr(), mask.data_ptr(), tuple(response.shape), injected, float(self.beta),
+                   self.person_offset)  # everything a capture bakes in by value
             one_graph = self.world_size == 1 or self.peer is not None
             if one_graph:
                 if self._replay((kind,) + key, lambda: body(response, mask, seed, e_i, e_a), True):

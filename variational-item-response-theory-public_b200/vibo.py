@@ -98,6 +98,12 @@ def build_parser():
     p.add_argument('--gpu-device', type=int, default=0)
     p.add_argument('--cuda', action='store_true', default=False)
     # additions
+    p.add_argument('--world-size', type=int, default=int(os.environ.get('WORLD_SIZE', '1')),
+                   help='person-sharded data parallelism: launch with torchrun, one process per GPU; every '
+                        'minibatch is split over the ranks, one all-reduce of [loss | grads] per step')
+    p.add_argument('--engine', type=str, default='trainer', choices=['trainer', 'autograd'],
+                   help="'trainer': ShardedElboTrainer (CUDA-graph step, fused Adam kernel, peer-memory "
+                        "all-reduce); 'autograd': model.fused_elbo + loss.backward() + torch.optim.Adam")
     p.add_argument('--reference-root', type=str, default=os.environ.get('VIBO_REF'),
                    help='checkout of the reference repo; needed only for the real-world datasets')
     return p
@@ -137,6 +143,14 @@ class ResidentDataset:
 
     def __len__(self):
         return self.num_person
+
+    def index_batches(self, batch_size, shuffle, generator=None):
+        """Row-index tensors of the epoch's minibatches (device side, one permutation per epoch)."""
+        n = self.num_person
+        order = torch.randperm(n, device=self.response.device, generator=generator) if shuffle \
+            else torch.arange(n, device=self.response.device)
+        for a in range(0, n, batch_size):
+            yield order[a:a + batch_size]
 
     def batches(self, batch_size, shuffle, generator=None):
         n = self.num_person
@@ -222,6 +236,14 @@ def main(argv=None):
 
     if not args.cuda:
         raise SystemExit("the B200 engine needs --cuda (there is no CPU fallback)")
+    world, rank = max(1, args.world_size), 0
+    if world > 1:
+        import torch.distributed as dist
+        rank = int(os.environ.get('RANK', '0'))
+        args.gpu_device = int(os.environ.get('LOCAL_RANK', str(rank)))
+        torch.cuda.set_device(args.gpu_device)
+        if not dist.is_initialized():
+            dist.init_process_group('nccl', device_id=torch.device('cuda', args.gpu_device))
     torch.cuda.set_device(args.gpu_device)
     device = torch.device('cuda', args.gpu_device)
 
@@ -249,31 +271,73 @@ def main(argv=None):
             return float(which + epoch * n_batches + 1) / float(args.epochs // 2 * n_batches)
         return args.beta_kl
 
-    def train(epoch):
-        model.train()
+    # ---- the hot loop (reference vibo.py:232-320) on the trainer: every minibatch is gathered into a
+    # static device buffer (two index_select launches) and the step itself -- zero_grad, fused ELBO
+    # forward/backward, all-reduce, Adam -- is ONE CUDA-graph replay; at world_size > 1 each rank
+    # takes its contiguous share of the batch.
+    from .distributed import ShardedElboTrainer, shard_bounds
+    trainer = None
+    if args.engine == 'trainer':
+        trainer = ShardedElboTrainer(model, lr=args.lr, world_size=world, rank=rank, beta=args.beta_kl,
+                                     use_kl_divergence=use_kl, cuda_graph=not args.anneal_kl, seed=args.seed)
+    elif world > 1:
+        raise SystemExit("--world-size > 1 needs --engine trainer")
+    static = {}
+
+    def local_rows(dataset, idx):
+        """This rank's share of the minibatch `idx`, gathered into static buffers (stable addresses,
+        so the captured graph of that batch shape is replayed)."""
+        lo, hi = shard_bounds(idx.numel(), rank, world)
+        n = hi - lo
+        key = (id(dataset), n)
+        if key not in static:
+            static[key] = (torch.empty(n, dataset.num_item, 1, device=device),
+                           torch.empty(n, dataset.num_item, 1, dtype=torch.bool, device=device))
+        r, m = static[key]
+        torch.index_select(dataset.response, 0, idx[lo:hi], out=r)
+        torch.index_select(dataset.mask, 0, idx[lo:hi], out=m)
+        return r, m, lo
+
+    def run_epoch(dataset, train_mode, epoch):
         total = torch.zeros((), device=device, dtype=torch.float64)
         seen = 0
-        for b, (response, mask) in enumerate(train_dataset.batches(args.batch_size, shuffle=True)):
-            optimizer.zero_grad(set_to_none=True)
-            loss = model.fused_elbo(response, mask, annealing_factor=annealing(epoch, b), use_kl_divergence=use_kl)
-            loss.backward()
-            optimizer.step()
-            total += loss.detach().double() * response.shape[0]   # no per-step host sync
-            seen += response.shape[0]
-        avg = float(total.item()) / seen
-        print('====> Train Epoch: {} Loss: {:.4f}'.format(epoch, avg))
+        # same permutation on every rank: torch's global generator is seeded identically (args.seed)
+        for b, idx in enumerate(dataset.index_batches(args.batch_size, shuffle=train_mode)):
+            response, mask, lo = local_rows(dataset, idx)
+            if trainer is not None:
+                trainer.person_offset = lo
+                if train_mode:
+                    trainer.beta = annealing(epoch, b)
+                    loss = trainer.train_step(response, mask)
+                else:
+                    trainer.beta = 1.0
+                    loss = trainer.eval_step(response, mask)
+            elif train_mode:
+                optimizer.zero_grad(set_to_none=True)
+                loss = model.fused_elbo(response, mask, annealing_factor=annealing(epoch, b),
+                                        use_kl_divergence=use_kl)
+                loss.backward()
+                optimizer.step()
+                loss = loss.detach()
+            else:
+                with torch.no_grad():
+                    loss = model.fused_elbo(response, mask, use_kl_divergence=use_kl)
+            total += loss.double() * idx.numel()   # no per-step host sync
+            seen += idx.numel()
+        return float(total.item()) / seen
+
+    def train(epoch):
+        model.train()
+        avg = run_epoch(train_dataset, True, epoch)
+        if rank == 0:
+            print('====> Train Epoch: {} Loss: {:.4f}'.format(epoch, avg))
         return avg
 
     def test(epoch):
         model.eval()
-        total = torch.zeros((), device=device, dtype=torch.float64)
-        seen = 0
-        with torch.no_grad():
-            for response, mask in test_dataset.batches(args.batch_size, shuffle=False):
-                total += model.fused_elbo(response, mask, use_kl_divergence=use_kl).double() * response.shape[0]
-                seen += response.shape[0]
-        avg = float(total.item()) / seen
-        print('====> Test Epoch: {} Loss: {:.4f}'.format(epoch, avg))
+        avg = run_epoch(test_dataset, False, epoch)
+        if rank == 0:
+            print('====> Test Epoch: {} Loss: {:.4f}'.format(epoch, avg))
         return avg
 
     def get_log_marginal_density(dataset):
@@ -344,6 +408,8 @@ def main(argv=None):
         else:
             is_best = train_losses[epoch] < best_loss
             best_loss = min(train_losses[epoch], best_loss)
+        if rank != 0:
+            continue
         save_checkpoint({'model_state_dict': model.state_dict(), 'epoch': epoch, 'args': args}, is_best,
                         folder=args.out_dir)
         np.save(os.path.join(args.out_dir, 'train_losses.npy'), train_losses)
@@ -351,6 +417,13 @@ def main(argv=None):
         if not args.no_test:
             np.save(os.path.join(args.out_dir, 'test_losses.npy'), test_losses)
 
+    if trainer is not None:
+        trainer.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        if rank != 0:
+            return
     for name in ['checkpoint.pth.tar', 'model_best.pth.tar']:
         path = os.path.join(args.out_dir, name)
         if not os.path.exists(path):
