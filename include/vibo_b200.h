@@ -259,6 +259,33 @@ int vibo_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, f
                    const int64_t* step, float lr, float beta1, float beta2, float eps, void* stream);
 
 /*
+ * Monte-Carlo estimators of the evaluation closures with the sample loop INSIDE the kernel (each
+ * row tile is read once and scored against all samples from shared memory):
+ *
+ *   vibo_log_marginal   VIBO_*PL.log_marginal (models.py:445-504) for the unconditional posterior:
+ *       log w_s = sum_i [ LL_i(theta_is, d_s) + log p(theta_is) - log q(theta_is) ] + log p(d_s) - log q(d_s)
+ *       (elbo(..., use_kl_divergence=False), models.py:432-441) with a fresh item draw d_s and fresh
+ *       ability draws theta_is per sample;  out_logp[0] = logsumexp_s(log w_s) - log(num_samples),
+ *       out_log_weights[s] = log w_s (doubles).  table (2, 1, 2D) as for vibo_fused_elbo;
+ *       item_mu / item_logvar (I, F) are item_encoder.{mu,logvar}_lookup.  Noise: eps_item
+ *       (S, I, F) and eps_ability (S, P, D) (either may be NULL: Philox with stream id s + 1,
+ *       key = seed, or seed_state[0] + seed_state[1] when seed_state is non-NULL; abilities keyed
+ *       by person_offset + row).
+ *   vibo_predictive_mean   mean over num_samples posterior draws of irt_model(theta_s, d_s)
+ *       (sample_posterior_predictive, vibo.py:349-390, followed by .mean(0), :515), given the
+ *       ability posterior (P, D) and the item posterior (I, F); out_mean (P, I).
+ */
+size_t vibo_log_marginal_workspace_bytes(int num_samples);
+int vibo_log_marginal(const vibo_desc* desc, const float* response, const uint8_t* mask, const float* table,
+                      const float* item_mu, const float* item_logvar, int num_samples,
+                      const float* eps_item, const float* eps_ability, uint64_t seed,
+                      const uint64_t* seed_state, double* out_log_weights, double* out_logp,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int vibo_predictive_mean(const vibo_desc* desc, const float* ability_mu, const float* ability_logvar,
+                         const float* item_mu, const float* item_logvar, int num_samples, uint64_t seed,
+                         const uint64_t* seed_state, float* out_mean, void* stream);
+
+/*
  * Planar normalizing flows on the abilities (--n-norm-flows K), per person and
  * fused with the reparameterised draw and the person-side terms of the flow
  * form of the ELBO [flows.py:21-41, :58-66; models.py:342-348, :406-424]:

@@ -412,6 +412,48 @@ int vibo_param_forward(const vibo_desc* desc, int hidden_dim, const float* mu_lo
   return VIBO_OK;
 }
 
+size_t vibo_log_marginal_workspace_bytes(int num_samples) {
+  return num_samples > 0 ? vibo::log_marginal_workspace_bytes(num_samples) : 0;
+}
+
+int vibo_log_marginal(const vibo_desc* desc, const float* response, const uint8_t* mask, const float* table,
+                      const float* item_mu, const float* item_logvar, int num_samples,
+                      const float* eps_item, const float* eps_ability, uint64_t seed,
+                      const uint64_t* seed_state, double* out_log_weights, double* out_logp,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (desc->conditional)
+    return fail(VIBO_ERR_UNSUPPORTED, "vibo_log_marginal covers the unconditional posterior (the table does not "
+                                      "depend on the item sample); compose per-sample calls otherwise");
+  if (num_samples < 1 || num_samples > 65536) return fail(VIBO_ERR_BAD_ARGUMENT, "num_samples must be in 1..65536");
+  if (!response || !mask || !table || !item_mu || !item_logvar || !out_log_weights || !out_logp)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (int rc = check_items(desc)) return rc;
+  if (desc->num_person == 0) return fail(VIBO_ERR_BAD_ARGUMENT, "num_person must be > 0");
+  if (workspace == nullptr || workspace_bytes < vibo::log_marginal_workspace_bytes(num_samples))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_log_marginal_workspace_bytes(num_samples)");
+  VIBO_CUDA(vibo::launch_log_marginal(*desc, num_samples, response, mask, table, item_mu, item_logvar, eps_item,
+                                      eps_ability, seed, seed_state, out_log_weights, out_logp, workspace,
+                                      workspace_bytes, static_cast<cudaStream_t>(stream)),
+            "log_marginal");
+  return VIBO_OK;
+}
+
+int vibo_predictive_mean(const vibo_desc* desc, const float* ability_mu, const float* ability_logvar,
+                         const float* item_mu, const float* item_logvar, int num_samples, uint64_t seed,
+                         const uint64_t* seed_state, float* out_mean, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (num_samples < 1) return fail(VIBO_ERR_BAD_ARGUMENT, "num_samples must be >= 1");
+  if (!ability_mu || !ability_logvar || !item_mu || !item_logvar || !out_mean)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (int rc = check_items(desc)) return rc;
+  if (desc->num_person == 0) return VIBO_OK;
+  VIBO_CUDA(vibo::launch_predictive_mean(*desc, num_samples, ability_mu, ability_logvar, item_mu, item_logvar, seed,
+                                         seed_state, out_mean, static_cast<cudaStream_t>(stream)),
+            "predictive_mean");
+  return VIBO_OK;
+}
+
 int vibo_param_forward_draw(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
                             const float* logvar_lookup, const uint64_t* seed_state, const float* w0,
                             const float* b0, const float* w2, const float* b2, const float* w4,

@@ -96,6 +96,16 @@ cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const fl
                                   float* g_mu, float* g_lv, float* g_w0, float* g_b0, float* g_w2,
                                   float* g_b2, float* g_w4, float* g_b4, cudaStream_t st);
 
+// vibo_sample.cu: sample-loop kernels (IWAE log-marginal, posterior-predictive mean)
+size_t log_marginal_workspace_bytes(int S);
+cudaError_t launch_log_marginal(const vibo_desc& d, int S, const float* resp, const uint8_t* mask, const float* table,
+                                const float* item_mu, const float* item_lv, const float* eps_item,
+                                const float* eps_ability, uint64_t seed, const uint64_t* seed_dev, double* log_w,
+                                double* out_logp, void* ws, size_t ws_bytes, cudaStream_t st);
+cudaError_t launch_predictive_mean(const vibo_desc& d, int S, const float* amu, const float* alv, const float* item_mu,
+                                   const float* item_lv, uint64_t seed, const uint64_t* seed_dev, float* out_mean,
+                                   cudaStream_t st);
+
 // vibo_fused.cu: single-pass kernel.  Returns false when the configuration is
 // not covered (caller composes the general kernels instead).
 void profile_begin();

@@ -317,3 +317,51 @@ def philox_normal(P, D, seed, person_offset, device):
                                             _stream(device))
     _lib.check(rc, "vibo_philox_normal")
     return out
+
+
+def log_marginal(response, mask, table, item_mu, item_logvar, num_samples, *, irt_model,
+                 missing_policy=MISSING_PRIOR, eps_item=None, eps_ability=None, seed=0, person_offset=0):
+    """vibo_log_marginal -> (logp 0-d f64, log_weights (S,) f64): IWAE bound with the sample loop in
+    the kernel (unconditional posterior)."""
+    _check_rows(response, mask)
+    lib = _lib.load()
+    P, I = response.shape
+    D = table.shape[-1] // 2
+    dev = response.device
+    desc = make_desc(P, I, D, irt_model, False, missing_policy, ELBO_SAMPLE, person_offset)
+    S = int(num_samples)
+    if eps_item is not None:
+        assert eps_item.shape == (S, I, item_feat_width(irt_model, D)) and eps_item.is_contiguous()
+    if eps_ability is not None:
+        assert eps_ability.shape == (S, P, D) and eps_ability.is_contiguous()
+    need = int(lib.vibo_log_marginal_workspace_bytes(S))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    log_w = torch.empty(S, dtype=torch.float64, device=dev)
+    logp = torch.empty(1, dtype=torch.float64, device=dev)
+    seed_t = seed if isinstance(seed, torch.Tensor) else None
+    rc = lib.vibo_log_marginal(C.byref(desc), _ptr(response), _ptr(mask), _ptr(table.contiguous()),
+                               _ptr(item_mu.contiguous()), _ptr(item_logvar.contiguous()), S, _ptr(eps_item),
+                               _ptr(eps_ability), C.c_uint64(0 if seed_t is not None else int(seed) & (2 ** 64 - 1)),
+                               _ptr(seed_t), _ptr(log_w), _ptr(logp), _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(rc, "vibo_log_marginal")
+    return logp[0], log_w
+
+
+def predictive_mean(ability_mu, ability_logvar, item_mu, item_logvar, num_samples, *, irt_model, seed=0,
+                    person_offset=0):
+    """vibo_predictive_mean -> (P, I) float32: mean over S posterior draws of the decoded response."""
+    if not ability_mu.is_cuda:
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    P, D = ability_mu.shape
+    I = item_mu.shape[0]
+    dev = ability_mu.device
+    desc = make_desc(P, I, D, irt_model, False, person_offset=person_offset)
+    out = torch.empty(P, I, dtype=torch.float32, device=dev)
+    seed_t = seed if isinstance(seed, torch.Tensor) else None
+    rc = _lib.load().vibo_predictive_mean(C.byref(desc), _ptr(ability_mu.contiguous()),
+                                          _ptr(ability_logvar.contiguous()), _ptr(item_mu.contiguous()),
+                                          _ptr(item_logvar.contiguous()), int(num_samples),
+                                          C.c_uint64(0 if seed_t is not None else int(seed) & (2 ** 64 - 1)),
+                                          _ptr(seed_t), _ptr(out), _stream(dev))
+    _lib.check(rc, "vibo_predictive_mean")
+    return out

@@ -332,13 +332,42 @@ class VIBO_1PL(nn.Module):
             + normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum()
         return (ll + log_p) - log_q
 
-    def log_marginal(self, response, mask, num_samples=100):
-        """reference models.py:445-504: logsumexp over num_samples batch-summed
-        log-weights - log(num_samples); each weight is one fused forward pass."""
+    def log_marginal(self, response, mask, num_samples=100, eps_item=None, eps_ability=None, seed=None):
+        """reference models.py:445-504: logsumexp over num_samples batch-summed log-weights -
+        log(num_samples) (0-d).  Unconditional product-of-experts posterior without flows on the
+        GPU: ONE kernel with the sample loop inside (``vibo_log_marginal``: rows read once, scored
+        against every sample from shared memory).  Otherwise each weight is one fused forward pass.
+        eps_item (S, I, F) / eps_ability (S, P, D): optional pre-drawn noise."""
         with torch.no_grad():
-            log_w = torch.stack([-self.fused_elbo(response, mask, use_kl_divergence=False)
-                                 for _ in range(num_samples)])
+            resp, msk = VF.prepare_rows(response, mask)
+            if (resp.is_cuda and self.ability_merge == 'product' and not self.conditional_posterior
+                    and self.n_norm_flows == 0):
+                if seed is None and (eps_item is None or eps_ability is None):
+                    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                item_mu, item_lv = self.item_encoder()
+                logp, _ = VF.K.log_marginal(resp, msk, self.ability_encoder.expert_table(), item_mu, item_lv,
+                                            num_samples, irt_model=self.irt_num,
+                                            missing_policy=self.ability_encoder.missing_policy,
+                                            eps_item=eps_item, eps_ability=eps_ability,
+                                            seed=0 if seed is None else seed)
+                return logp.to(torch.float32)
+            log_w = torch.stack([-self.fused_elbo(
+                response, mask, use_kl_divergence=False,
+                eps_item=None if eps_item is None else eps_item[s],
+                eps_ability=None if eps_ability is None else eps_ability[s])
+                for s in range(num_samples)])
             return torch.logsumexp(log_w, 0) - math.log(num_samples)
+
+    def posterior_predictive_mean(self, response, mask, num_samples=100, seed=None):
+        """mean over num_samples posterior draws of decode(ability_s, item_feat_s) -> (P, I, 1):
+        sample_posterior_predictive + .mean(0) of the reference (vibo.py:349-390, :515) in one kernel
+        (``vibo_predictive_mean``) instead of S decodes stacked on the host."""
+        with torch.no_grad():
+            _, a_mu, a_lv, _, i_mu, i_lv = self.encode(response, mask)
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            out = VF.K.predictive_mean(a_mu, a_lv, i_mu, i_lv, num_samples, irt_model=self.irt_num, seed=seed)
+            return out.unsqueeze(2)
 
     # ------------------------------------------------------------ fused entry
     def fused_elbo(self, response, mask, annealing_factor=1, use_kl_divergence=True, eps_item=None,

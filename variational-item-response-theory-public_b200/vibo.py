@@ -9,8 +9,12 @@ test_losses.npy), with the hot loop replaced:
   permutation + row gathers instead of a DataLoader calling a per-person
   ``__getitem__`` (SURVEY.md 8f1);
 * a training step is ``model.fused_elbo`` (one pass over the batch rows);
-* posterior-predictive imputation accumulates the mean of the decoded samples
-  on the GPU instead of stacking (S, P, I, 1) on the host.
+* a training step is one CUDA-graph replay of ``ShardedElboTrainer`` (``--engine trainer``);
+* ``log_marginal`` and the posterior-predictive mean run the S-sample loop inside one kernel;
+* posterior-predictive imputation stores the mean of the decoded samples
+  (``checkpoint['posterior_predict_mean']``) instead of stacking (S, P, I, 1) on the host --
+  DEVIATION from the reference's ``checkpoint['posterior_predict_samples']`` (vibo.py:497-498);
+  pass ``--save-predictive-samples`` to write that key as well.
 
     python -m vibo_b200.vibo --irt-model 2pl --dataset 2pl_simulation \\
         --num-person 10000 --num-item 100 --ability-dim 1 --cuda --epochs 5
@@ -104,6 +108,10 @@ def build_parser():
     p.add_argument('--engine', type=str, default='trainer', choices=['trainer', 'autograd'],
                    help="'trainer': ShardedElboTrainer (CUDA-graph step, fused Adam kernel, peer-memory "
                         "all-reduce); 'autograd': model.fused_elbo + loss.backward() + torch.optim.Adam")
+    p.add_argument('--save-predictive-samples', action='store_true', default=False,
+                   help="also store checkpoint['posterior_predict_samples'] = {'response': (S, P, I, 1)} as the "
+                        "reference does (vibo.py:497-498); default: only the mean over the S draws "
+                        "('posterior_predict_mean'), computed on the GPU")
     p.add_argument('--reference-root', type=str, default=os.environ.get('VIBO_REF'),
                    help='checkout of the reference repo; needed only for the real-world datasets')
     return p
@@ -364,20 +372,31 @@ def main(argv=None):
                 'item_feat_mu': i_mu.cpu(), 'item_feat_logvar': i_lv.cpu()}
 
     def posterior_predictive_mean(dataset, num_samples):
-        """mean over S posterior draws of decode(ability_s, item_feat_s) (reference
-        vibo.py:349-390 stacks the S samples on the host and averages later, :515)."""
+        """mean over S posterior draws of decode(ability_s, item_feat_s) (reference vibo.py:349-390
+        stacks the S samples on the host and averages later, :515): one kernel per batch with the
+        sample loop inside (vibo_predictive_mean)."""
         model.eval()
         outs = []
+        for response, mask in dataset.batches(max(args.batch_size, 4096), shuffle=False):
+            outs.append(model.posterior_predictive_mean(response, mask, num_samples).cpu())
+        return torch.cat(outs)
+
+    def posterior_predictive_samples(dataset, num_samples):
+        """reference-format output of sample_posterior_predictive (vibo.py:349-390):
+        {'response': (S, P, I, 1)} on the host -- only with --save-predictive-samples (S x the
+        dataset in host memory)."""
+        model.eval()
+        sets = []
         with torch.no_grad():
             for response, mask in dataset.batches(args.batch_size, shuffle=False):
                 _, a_mu, a_lv, _, i_mu, i_lv = model.encode(response, mask)
-                acc = torch.zeros(response.shape[0], num_item, 1, device=device)
+                samples = []
                 for _ in range(num_samples):
                     ability = a_mu + torch.exp(0.5 * a_lv) * torch.randn_like(a_mu)
                     item = i_mu + torch.exp(0.5 * i_lv) * torch.randn_like(i_mu)
-                    acc += model.decode(ability, item)
-                outs.append((acc / num_samples).cpu())
-        return torch.cat(outs)
+                    samples.append(model.decode(ability, item).cpu())
+                sets.append(torch.stack(samples))
+        return {'response': torch.cat(sets, dim=1)}
 
     def posterior_mean_response(dataset):
         # reference vibo.py:392-418
@@ -433,7 +452,13 @@ def main(argv=None):
         if not args.no_infer_dict:
             checkpoint['infer_dict'] = get_infer_dict(train_dataset)
         if not args.no_predictive:
-            pred = posterior_predictive_mean(train_dataset, args.num_posterior_samples)
+            if args.save_predictive_samples:
+                # the key the reference's analysis scripts read (vibo.py:497-498)
+                checkpoint['posterior_predict_samples'] = posterior_predictive_samples(
+                    train_dataset, args.num_posterior_samples)
+                pred = checkpoint['posterior_predict_samples']['response'].mean(0)
+            else:
+                pred = posterior_predictive_mean(train_dataset, args.num_posterior_samples)
             checkpoint['posterior_predict_mean'] = pred
             if args.artificial_missing_perc > 0:
                 acc = imputation_accuracy(pred)
