@@ -143,6 +143,23 @@ int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
                          void* stream);
 
 /*
+ * Packed row format: one signed byte per cell, -1 = missing (src/config.py:14), 0 / 1 = observed
+ * response -- the (response, mask) pair of src/datasets.py:928-940 in 1 byte instead of 5.
+ *   vibo_pack / vibo_unpack   device-side conversion between the pair and the packed rows (P, I).
+ *   vibo_fused_elbo_host_packed   vibo_fused_elbo_host with the rows in HOST memory in the packed
+ *       format: PCIe carries 1 B/cell; each chunk is expanded on the device (one streaming kernel)
+ *       before the row kernels read it.  Same staging size query (vibo_host_staging_bytes).
+ */
+int vibo_pack(const vibo_desc* desc, const float* response, const uint8_t* mask, int8_t* packed, void* stream);
+int vibo_unpack(const vibo_desc* desc, const int8_t* packed, float* response, uint8_t* mask, void* stream);
+int vibo_fused_elbo_host_packed(const vibo_desc* desc, const int8_t* packed_host, const float* table,
+                                const float* item_feat, const float* eps_ability, uint64_t seed,
+                                float beta, double* out_scalars, double* out_scalars_host,
+                                float* g_table, float* g_item, int64_t chunk_person, void* staging,
+                                size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/*
  * encode: product-of-experts ability posterior only.
  * Replaces AbilityInferenceNetwork._forward_product (models.py:596-629) +
  * product_of_experts (utils.py:105-113).  precision_sum (P, D) = sum of expert

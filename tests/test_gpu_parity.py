@@ -412,3 +412,40 @@ def test_paths_agree_on_random_shapes(vb, monkeypatch, P, I, D, irt, cond, missi
         assert rel_l2(a["g_table"], b["g_table"]) < TOL
     for k in ("ability_mu", "ability_logvar", "ability"):
         assert max_rel(a[k][fin], b[k][fin]) < TOL, k
+
+
+def test_packed_rows_roundtrip_and_host_entry(vb):
+    """Packed row format (int8 -1 / 0 / 1): pack -> unpack is the identity on (observed response,
+    mask); the packed host entry and packed device rows give the result of the unpacked rows."""
+    P, I, D = 5003, 100, 1
+    resp, mask, table, item, eps = _synth(P, I, D, 2, False, 0.1, seed=33)
+    dev = "cuda"
+    r, m = torch.from_numpy(resp).to(dev), torch.from_numpy(mask).to(dev)
+    pk = vb.kernels.pack_rows(r, m)
+    assert pk.dtype == torch.int8 and pk.shape == (P, I)
+    want = np.where(mask != 0, (resp > 0.5).astype(np.int8), np.int8(-1))
+    assert np.array_equal(pk.cpu().numpy(), want)
+    assert np.array_equal(vb.kernels.pack_rows_host(torch.from_numpy(resp), torch.from_numpy(mask)).numpy(), want)
+    r2, m2 = vb.kernels.unpack_rows(pk)
+    assert np.array_equal(m2.cpu().numpy(), (mask != 0).astype(np.uint8))
+    assert np.array_equal(r2.cpu().numpy()[mask != 0], resp[mask != 0])
+    assert np.all(r2.cpu().numpy()[mask == 0] == -1.0)
+    devres = _run_fused(vb, resp, mask, table, item, eps, irt_model=2, conditional=False)
+    out = vb.kernels.fused_elbo_host(pk.cpu().pin_memory(), None, torch.from_numpy(table).to(dev),
+                                     torch.from_numpy(item).to(dev), torch.from_numpy(eps).to(dev),
+                                     irt_model=2, conditional=False, chunk_person=1024)
+    torch.cuda.synchronize()
+    assert rel_l2(out["scalars_host"].numpy(), devres["scalars"]) < 1e-6
+    assert rel_l2(out["g_item"].cpu().numpy(), devres["g_item"]) < 1e-6
+    # module level: packed rows on the device and on the host
+    import vibo_b200
+    torch.manual_seed(0)
+    model = vibo_b200.VIBO_2PL(1, I, ability_merge="product").to(dev)
+    e_i = torch.randn(I, 2, device=dev)
+    e_a = torch.from_numpy(eps).to(dev)
+    with torch.no_grad():
+        a = model.fused_elbo(r.unsqueeze(2), m.bool().unsqueeze(2), eps_item=e_i, eps_ability=e_a)
+        b = model.fused_elbo(pk, None, eps_item=e_i, eps_ability=e_a)
+        c = model.fused_elbo(pk.cpu(), None, eps_item=e_i, eps_ability=e_a)
+    assert float(a) == float(b)
+    assert abs(float(a) - float(c)) <= 1e-6 * abs(float(a))

@@ -47,6 +47,10 @@ SIGNATURES = {
     "vibo_host_staging_bytes": (C.c_size_t, [_PD, C.c_int64]),
     "vibo_fused_elbo_host": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_uint64, C.c_float, _p, _p, _p, _p,
                                        C.c_int64, _p, C.c_size_t, _p, C.c_size_t, _p]),
+    "vibo_fused_elbo_host_packed": (C.c_int, [_PD, _p, _p, _p, _p, C.c_uint64, C.c_float, _p, _p, _p, _p,
+                                              C.c_int64, _p, C.c_size_t, _p, C.c_size_t, _p]),
+    "vibo_pack": (C.c_int, [_PD, _p, _p, _p, _p]),
+    "vibo_unpack": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_encode": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p]),
     "vibo_person_counts": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_encode_backward": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),

@@ -34,7 +34,7 @@ struct HostPipe {
 thread_local HostPipe g_pipe;
 
 struct StagingLayout {
-  size_t resp[2], mask[2], scalars, g_table, g_item, total;
+  size_t resp[2], mask[2], packed[2], scalars, g_table, g_item, total;
 };
 
 StagingLayout staging_layout(const vibo_desc& d, int64_t chunk) {
@@ -45,6 +45,9 @@ StagingLayout staging_layout(const vibo_desc& d, int64_t chunk) {
   for (int b = 0; b < 2; ++b) {
     L.resp[b] = off; off += align_up(cells * 4, 256);
     L.mask[b] = off; off += align_up(cells, 256);
+  }
+  for (int b = 0; b < 2; ++b) {
+    L.packed[b] = off; off += align_up(cells, 256);  // landing buffers of the packed transfer format
   }
   L.scalars = off; off += 256;
   L.g_table = off; off += align_up(4 * 2 * (size_t)(d.conditional ? d.num_item : 1) * 2 * d.ability_dim, 256);
@@ -62,14 +65,15 @@ size_t vibo_host_staging_bytes(const vibo_desc* desc, int64_t chunk_person) {
   return staging_layout(*desc, chunk_person).total;
 }
 
-int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
-                         const uint8_t* mask_host, const float* table, const float* item_feat,
-                         const float* eps_ability, uint64_t seed, float beta,
-                         double* out_scalars, double* out_scalars_host, float* g_table,
-                         float* g_item, int64_t chunk_person, void* staging,
-                         size_t staging_bytes, void* workspace, size_t workspace_bytes,
-                         void* stream) {
-  if (desc == nullptr || response_host == nullptr || mask_host == nullptr || staging == nullptr ||
+static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_host,
+                                const uint8_t* mask_host, const int8_t* packed_host, const float* table,
+                                const float* item_feat, const float* eps_ability, uint64_t seed, float beta,
+                                double* out_scalars, double* out_scalars_host, float* g_table,
+                                float* g_item, int64_t chunk_person, void* staging,
+                                size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  const bool packed = packed_host != nullptr;
+  if (desc == nullptr || (!packed && (response_host == nullptr || mask_host == nullptr)) || staging == nullptr ||
       out_scalars == nullptr || chunk_person <= 0)
     return vibo::set_last_error(VIBO_ERR_BAD_ARGUMENT,
                                 "vibo_fused_elbo_host: desc, response_host, mask_host, staging and out_scalars "
@@ -110,14 +114,25 @@ int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
     const int b = (int)(c & 1);
     const int64_t n = (d.num_person - r0 < chunk_person) ? d.num_person - r0 : chunk_person;
     if (c >= 2) VIBO_HOST_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0), "stream wait");
-    VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.resp[b], response_host + (size_t)r0 * d.num_item,
-                                   (size_t)n * d.num_item * sizeof(float), cudaMemcpyHostToDevice, g_pipe.copy),
-                   "H2D copy of response rows");
-    VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item, (size_t)n * d.num_item,
-                                   cudaMemcpyHostToDevice, g_pipe.copy),
-                   "H2D copy of mask rows");
+    if (packed) {
+      VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.packed[b], packed_host + (size_t)r0 * d.num_item,
+                                     (size_t)n * d.num_item, cudaMemcpyHostToDevice, g_pipe.copy),
+                     "H2D copy of packed rows");
+    } else {
+      VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.resp[b], response_host + (size_t)r0 * d.num_item,
+                                     (size_t)n * d.num_item * sizeof(float), cudaMemcpyHostToDevice, g_pipe.copy),
+                     "H2D copy of response rows");
+      VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item, (size_t)n * d.num_item,
+                                     cudaMemcpyHostToDevice, g_pipe.copy),
+                     "H2D copy of mask rows");
+    }
     VIBO_HOST_CUDA(cudaEventRecord(g_pipe.copied[b], g_pipe.copy), "event record");
     VIBO_HOST_CUDA(cudaStreamWaitEvent(st, g_pipe.copied[b], 0), "stream wait");
+    if (packed)  // 1 B/cell crossed PCIe; expand to the (response, mask) pair the row kernels read
+      VIBO_HOST_CUDA(vibo::launch_unpack(n * d.num_item, reinterpret_cast<const int8_t*>(base + L.packed[b]),
+                                         reinterpret_cast<float*>(base + L.resp[b]),
+                                         reinterpret_cast<uint8_t*>(base + L.mask[b]), st),
+                     "unpack");
     vibo_desc dc = d;
     dc.num_person = n;
     dc.person_offset = d.person_offset + r0;
@@ -142,6 +157,53 @@ int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
                    "D2H copy of the scalars");
   VIBO_HOST_CUDA(cudaStreamSynchronize(st), "stream synchronize");
 #undef VIBO_HOST_CUDA
+  return VIBO_OK;
+}
+
+int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
+                         const uint8_t* mask_host, const float* table, const float* item_feat,
+                         const float* eps_ability, uint64_t seed, float beta,
+                         double* out_scalars, double* out_scalars_host, float* g_table,
+                         float* g_item, int64_t chunk_person, void* staging,
+                         size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return fused_elbo_host_impl(desc, response_host, mask_host, nullptr, table, item_feat, eps_ability, seed, beta,
+                              out_scalars, out_scalars_host, g_table, g_item, chunk_person, staging,
+                              staging_bytes, workspace, workspace_bytes, stream);
+}
+
+int vibo_fused_elbo_host_packed(const vibo_desc* desc, const int8_t* packed_host, const float* table,
+                                const float* item_feat, const float* eps_ability, uint64_t seed,
+                                float beta, double* out_scalars, double* out_scalars_host,
+                                float* g_table, float* g_item, int64_t chunk_person, void* staging,
+                                size_t staging_bytes, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (packed_host == nullptr)
+    return vibo::set_last_error(VIBO_ERR_BAD_ARGUMENT, "vibo_fused_elbo_host_packed: packed_host is NULL");
+  return fused_elbo_host_impl(desc, nullptr, nullptr, packed_host, table, item_feat, eps_ability, seed, beta,
+                              out_scalars, out_scalars_host, g_table, g_item, chunk_person, staging,
+                              staging_bytes, workspace, workspace_bytes, stream);
+}
+
+int vibo_pack(const vibo_desc* desc, const float* response, const uint8_t* mask, int8_t* packed, void* stream) {
+  if (desc == nullptr || response == nullptr || mask == nullptr || packed == nullptr || desc->num_person < 0 ||
+      desc->num_item <= 0)
+    return vibo::set_last_error(VIBO_ERR_BAD_ARGUMENT, "vibo_pack: bad argument");
+  if (desc->num_person == 0) return VIBO_OK;
+  if (vibo::launch_pack(desc->num_person * (int64_t)desc->num_item, response, mask, packed,
+                        static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return vibo::set_last_error(VIBO_ERR_CUDA, "vibo_pack: launch failed");
+  return VIBO_OK;
+}
+
+int vibo_unpack(const vibo_desc* desc, const int8_t* packed, float* response, uint8_t* mask, void* stream) {
+  if (desc == nullptr || response == nullptr || mask == nullptr || packed == nullptr || desc->num_person < 0 ||
+      desc->num_item <= 0)
+    return vibo::set_last_error(VIBO_ERR_BAD_ARGUMENT, "vibo_unpack: bad argument");
+  if (desc->num_person == 0) return VIBO_OK;
+  if (vibo::launch_unpack(desc->num_person * (int64_t)desc->num_item, packed, response, mask,
+                          static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return vibo::set_last_error(VIBO_ERR_CUDA, "vibo_unpack: launch failed");
   return VIBO_OK;
 }
 

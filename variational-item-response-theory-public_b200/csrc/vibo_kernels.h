@@ -96,6 +96,10 @@ cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const fl
                                   float* g_mu, float* g_lv, float* g_w0, float* g_b0, float* g_w2,
                                   float* g_b2, float* g_w4, float* g_b4, cudaStream_t st);
 
+// vibo_pack.cu: one-byte-per-cell row format
+cudaError_t launch_pack(int64_t n, const float* resp, const uint8_t* mask, int8_t* out, cudaStream_t st);
+cudaError_t launch_unpack(int64_t n, const int8_t* in, float* resp, uint8_t* mask, cudaStream_t st);
+
 // vibo_sample.cu: sample-loop kernels (IWAE log-marginal, posterior-predictive mean)
 size_t log_marginal_workspace_bytes(int S);
 cudaError_t launch_log_marginal(const vibo_desc& d, int S, const float* resp, const uint8_t* mask, const float* table,

@@ -24,6 +24,13 @@ def prepare_rows(response: torch.Tensor, mask: torch.Tensor):
     if response.dim() == 3:
         response = response.view(response.shape[0], response.shape[1]) if response.is_contiguous() \
             else response.reshape(response.shape[0], response.shape[1])
+    if response.dtype == torch.int8:
+        # packed rows (-1 missing / 0 / 1, one byte per cell): host tensors stay packed (the host
+        # entry transfers them as they are), device tensors are expanded by vibo_unpack
+        response = response.contiguous()
+        if not response.is_cuda:
+            return response, None
+        return K.unpack_rows(response)
     if mask.dim() == 3:
         mask = mask.reshape(mask.shape[0], mask.shape[1])
     if response.dtype != torch.float32:

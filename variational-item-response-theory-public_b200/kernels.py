@@ -106,9 +106,12 @@ def fused_elbo_host(response_host, mask_host, table, item_feat, eps_ability, *, 
     """vibo_fused_elbo_host: response/mask are HOST tensors (pinned for full
     copy bandwidth); returns the same dict as fused_elbo plus ``scalars_host``."""
     lib = _lib.load()
-    assert not response_host.is_cuda and not mask_host.is_cuda
-    assert response_host.dtype == torch.float32 and response_host.is_contiguous()
-    assert mask_host.dtype == torch.uint8 and mask_host.is_contiguous()
+    packed = response_host.dtype == torch.int8   # one byte per cell (-1 missing / 0 / 1), mask_host unused
+    assert not response_host.is_cuda and response_host.is_contiguous()
+    if not packed:
+        assert not mask_host.is_cuda
+        assert response_host.dtype == torch.float32
+        assert mask_host.dtype == torch.uint8 and mask_host.is_contiguous()
     P, I = response_host.shape
     D = table.shape[-1] // 2
     dev = table.device
@@ -122,13 +125,21 @@ def fused_elbo_host(response_host, mask_host, table, item_feat, eps_ability, *, 
     g_table = torch.empty_like(table) if want_grads else None
     g_item = torch.empty_like(item_feat) if want_grads else None
     ws = workspace(desc, dev)
-    rc = lib.vibo_fused_elbo_host(C.byref(desc), _ptr(response_host), _ptr(mask_host), _ptr(table),
-                                  _ptr(item_feat), _ptr(eps_ability),
-                                  C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(beta), _ptr(scalars),
-                                  _ptr(scalars_host), _ptr(g_table), _ptr(g_item),
-                                  C.c_int64(chunk_person), _ptr(staging), staging.numel(), _ptr(ws),
-                                  ws.numel(), _stream(dev))
-    _lib.check(rc, "vibo_fused_elbo_host")
+    if packed:
+        rc = lib.vibo_fused_elbo_host_packed(C.byref(desc), _ptr(response_host), _ptr(table), _ptr(item_feat),
+                                             _ptr(eps_ability), C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                             C.c_float(beta), _ptr(scalars), _ptr(scalars_host), _ptr(g_table),
+                                             _ptr(g_item), C.c_int64(chunk_person), _ptr(staging),
+                                             staging.numel(), _ptr(ws), ws.numel(), _stream(dev))
+        _lib.check(rc, "vibo_fused_elbo_host_packed")
+    else:
+        rc = lib.vibo_fused_elbo_host(C.byref(desc), _ptr(response_host), _ptr(mask_host), _ptr(table),
+                                      _ptr(item_feat), _ptr(eps_ability),
+                                      C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_float(beta), _ptr(scalars),
+                                      _ptr(scalars_host), _ptr(g_table), _ptr(g_item),
+                                      C.c_int64(chunk_person), _ptr(staging), staging.numel(), _ptr(ws),
+                                      ws.numel(), _stream(dev))
+        _lib.check(rc, "vibo_fused_elbo_host")
     return dict(scalars=scalars, scalars_host=scalars_host, g_table=g_table, g_item=g_item,
                 staging=staging)
 
@@ -365,3 +376,37 @@ def predictive_mean(ability_mu, ability_logvar, item_mu, item_logvar, num_sample
                                           _ptr(seed_t), _ptr(out), _stream(dev))
     _lib.check(rc, "vibo_predictive_mean")
     return out
+
+
+def pack_rows(response, mask):
+    """vibo_pack: (P, I) float32 response + uint8 mask on the GPU -> (P, I) int8 (-1 missing / 0 / 1)."""
+    _check_rows(response, mask)
+    P, I = response.shape
+    desc = make_desc(P, I, 1, 1, False)
+    out = torch.empty(P, I, dtype=torch.int8, device=response.device)
+    rc = _lib.load().vibo_pack(C.byref(desc), _ptr(response), _ptr(mask), _ptr(out), _stream(response.device))
+    _lib.check(rc, "vibo_pack")
+    return out
+
+
+def unpack_rows(packed):
+    """vibo_unpack: (P, I) int8 on the GPU -> ((P, I) float32 response, (P, I) uint8 mask)."""
+    if not packed.is_cuda:
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    assert packed.dtype == torch.int8 and packed.dim() == 2 and packed.is_contiguous()
+    P, I = packed.shape
+    desc = make_desc(P, I, 1, 1, False)
+    resp = torch.empty(P, I, dtype=torch.float32, device=packed.device)
+    mask = torch.empty(P, I, dtype=torch.uint8, device=packed.device)
+    rc = _lib.load().vibo_unpack(C.byref(desc), _ptr(packed), _ptr(resp), _ptr(mask), _stream(packed.device))
+    _lib.check(rc, "vibo_unpack")
+    return resp, mask
+
+
+def pack_rows_host(response, mask):
+    """Host-side packing of dataset arrays (done once at load): (P, I[, 1]) response + mask ->
+    pinned (P, I) int8 in the packed row format."""
+    r = response.reshape(response.shape[0], response.shape[1])
+    m = mask.reshape(mask.shape[0], mask.shape[1]) != 0
+    out = torch.where(m, (r > 0.5).to(torch.int8), torch.full((), -1, dtype=torch.int8))
+    return out.contiguous().pin_memory() if torch.cuda.is_available() else out.contiguous()
