@@ -35,7 +35,7 @@ def _import_reference():
     return models
 
 
-def synth_responses(P, I, D, irt_model, seed, missing_frac):
+def synth_responses(P, I, D, irt_model, seed, missing_frac, continuous=False):
     """Plain-torch restatement of the generative draw of
     src/pyro_core/models.py:68-110 (abilities, then item features, then
     Bernoulli responses) + src/datasets.py:46-78 style masking."""
@@ -52,6 +52,8 @@ def synth_responses(P, I, D, irt_model, seed, missing_frac):
         gs = torch.sigmoid(item[:, D + 1]).unsqueeze(0)
         p = gs + (1 - gs) * p
     resp = torch.bernoulli(p, generator=g)
+    if continuous:   # --response-dist gaussian: real-valued responses around the link probability
+        resp = p + 0.1 * torch.randn(P, I, generator=g)
     mask = torch.ones(P, I, dtype=torch.bool)
     if missing_frac > 0:
         mask = torch.rand(P, I, generator=g) >= missing_frac
@@ -65,10 +67,13 @@ CASES = []
 
 
 def case(name, irt, D, cond, P, I, missing=0.0, drop=False, beta=1.0, use_kl=True,
-         flows=0, trained_like=False, seed=0, merge="product"):
-    CASES.append(dict(name=name, irt_model=irt, ability_dim=D, conditional=cond, P=P, I=I,
-                      missing_frac=missing, drop_missing=drop, beta=beta, use_kl=use_kl,
-                      n_flows=flows, trained_like=trained_like, seed=seed, merge=merge))
+         flows=0, trained_like=False, seed=0, merge="product", generative="irt", response_dist="bernoulli"):
+    c = dict(name=name, irt_model=irt, ability_dim=D, conditional=cond, P=P, I=I,
+             missing_frac=missing, drop_missing=drop, beta=beta, use_kl=use_kl,
+             n_flows=flows, trained_like=trained_like, seed=seed, merge=merge)
+    if generative != "irt" or response_dist != "bernoulli":   # keys only where they differ from the defaults
+        c.update(generative=generative, response_dist=response_dist)
+    CASES.append(c)
 
 
 # --- the grid (small enough that the whole CPU suite stays in seconds) -----
@@ -103,6 +108,24 @@ case("m1pl_d3_cond_mean_miss", 1, 3, True, 20, 15, missing=0.2, use_kl=False, me
      seed=304)
 case("m2pl_d1_unc_mean_flows2", 2, 1, False, 18, 14, flows=2, use_kl=False, merge="mean", trained_like=True,
      seed=305)
+# nonlinear generative models (models.py:769-919) and Gaussian responses (models.py:400-402,
+# utils.py:52-56): SURVEY.md 8 rows f3 / f4
+case("m2pl_d1_unc_link_full", 2, 1, False, 20, 16, generative="link", trained_like=True, seed=401)
+case("m3pl_d2_cond_link_miss", 3, 2, True, 17, 13, missing=0.15, beta=0.7, generative="link", trained_like=True,
+     seed=402)
+case("m1pl_d1_unc_deep_full", 1, 1, False, 18, 15, generative="deep", trained_like=True, seed=403)
+case("m2pl_d2_unc_deep_miss", 2, 2, False, 16, 14, missing=0.2, use_kl=False, generative="deep", trained_like=True,
+     seed=404)
+case("m2pl_d1_unc_residual_full", 2, 1, False, 19, 12, generative="residual", trained_like=True, seed=405)
+case("m3pl_d2_unc_residual_miss", 3, 2, False, 15, 16, missing=0.1, generative="residual", trained_like=True,
+     seed=406)
+case("m2pl_d1_unc_gauss_full", 2, 1, False, 18, 14, response_dist="gaussian", trained_like=True, seed=407)
+case("m2pl_d2_cond_gauss_miss", 2, 2, True, 16, 12, missing=0.15, beta=0.7, response_dist="gaussian",
+     trained_like=True, seed=408)
+case("m1pl_d1_unc_gauss_mean_miss", 1, 1, False, 17, 11, missing=0.1, merge="mean", response_dist="gaussian",
+     trained_like=True, seed=409)
+case("m2pl_d1_unc_gauss_drop_link", 2, 1, False, 15, 13, missing=0.2, drop=True, generative="link",
+     response_dist="gaussian", trained_like=True, seed=410)
 
 
 def run_case(models, c):
@@ -111,7 +134,7 @@ def run_case(models, c):
     cls = {1: models.VIBO_1PL, 2: models.VIBO_2PL, 3: models.VIBO_3PL}[irt]
     torch.manual_seed(c["seed"])
     model = cls(D, I, hidden_dim=64, ability_merge=c.get("merge", "product"), conditional_posterior=cond,
-                generative_model="irt", response_dist="bernoulli",
+                generative_model=c.get("generative", "irt"), response_dist=c.get("response_dist", "bernoulli"),
                 replace_missing_with_prior=not c["drop_missing"], n_norm_flows=c["n_flows"])
     init_state = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
     if c["trained_like"]:
@@ -123,7 +146,8 @@ def run_case(models, c):
             model.item_encoder.mu_lookup.weight[:, 1] = torch.linspace(-30, 30, I)
             model.item_encoder.logvar_lookup.weight.fill_(-8.0)
     Fw = model.item_feat_dim
-    response, mask_b = synth_responses(P, I, D, irt, c["seed"] + 1000, c["missing_frac"])
+    response, mask_b = synth_responses(P, I, D, irt, c["seed"] + 1000, c["missing_frac"],
+                                       continuous=c.get("response_dist") == "gaussian")
     mask = mask_b.long()
     g = torch.Generator().manual_seed(c["seed"] + 2000)
     eps_item = torch.randn(I, Fw, generator=g)
@@ -224,6 +248,30 @@ def run_log_marginal(models):
     return rec
 
 
+def run_vi(models):
+    """Un-amortized VI_2PL (models.py:89-243): forward(index, response, mask) + elbo + backward."""
+    torch.manual_seed(91)
+    P_all, I, D, P = 40, 13, 2, 12
+    model = models.VI_2PL(D, P_all, I)
+    response, mask_b = synth_responses(P, I, D, 2, 1091, 0.15)
+    index = torch.tensor([3, 7, 39, 0, 11, 12, 20, 21, 22, 5, 6, 30])
+    g = torch.Generator().manual_seed(2091)
+    eps_item, eps_ability = torch.randn(I, D + 1, generator=g), torch.randn(P, D, generator=g)
+    queue = [eps_item, eps_ability]
+    model.reparameterize_gaussian = lambda mean, logvar: queue.pop(0).mul(torch.exp(0.5 * logvar)).add_(mean)
+    out = model(index, response, mask_b.long())
+    loss = model.elbo(*out, annealing_factor=0.7, use_kl_divergence=True)
+    loss.backward()
+    rec = dict(index=index.numpy(), response=response.numpy()[:, :, 0], mask=mask_b.numpy()[:, :, 0].astype(np.uint8),
+               eps_item=eps_item.numpy(), eps_ability=eps_ability.numpy(), loss=np.float64(loss.item()),
+               response_mu=out[2].detach().numpy()[:, :, 0], beta=np.float64(0.7))
+    for k, v in model.state_dict().items():
+        rec["param/" + k] = v.detach().numpy()
+    for k, v in model.named_parameters():
+        rec["grad/" + k] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()
+    return rec
+
+
 def run_mask_fixture():
     """artificially_mask_dataset of the reference (src/datasets.py:46-78) on a toy
     dataset object; nltk is a dead import there (datasets.py:8) and is stubbed."""
@@ -257,6 +305,8 @@ def main():
         print(f"{c['name']:40s} loss={float(rec['loss']):.6f}")
     if regenerate_all or not os.path.exists(os.path.join(HERE, "log_marginal_2pl_d2.npz")):
         np.savez_compressed(os.path.join(HERE, "log_marginal_2pl_d2.npz"), **run_log_marginal(models))
+    if regenerate_all or not os.path.exists(os.path.join(HERE, "vi_2pl_d2.npz")):
+        np.savez_compressed(os.path.join(HERE, "vi_2pl_d2.npz"), **run_vi(models))
     if regenerate_all or not os.path.exists(os.path.join(HERE, "artificial_mask.npz")):
         np.savez_compressed(os.path.join(HERE, "artificial_mask.npz"), **run_mask_fixture())
     with open(os.path.join(HERE, "index.json"), "w") as f:

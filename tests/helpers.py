@@ -11,6 +11,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 with open(os.path.join(GOLDEN, "index.json")) as _f:
     CASES = json.load(_f)["cases"]
 CASE_NAMES = [c["name"] for c in CASES]
+# cases of the path the oracle (oracle/reference_port.py, oracle/kernel_spec.py) restates: IRT link,
+# Bernoulli responses.  The nonlinear decoders / Gaussian responses are pinned by
+# the live-reference fixtures directly.
+PORT_CASE_NAMES = [c["name"] for c in CASES if "generative" not in c]
 CASE_BY_NAME = {c["name"]: c for c in CASES}
 
 
@@ -46,7 +50,8 @@ def build_model(cfg, params, device="cpu"):
     import vibo_b200
     cls = {1: vibo_b200.VIBO_1PL, 2: vibo_b200.VIBO_2PL, 3: vibo_b200.VIBO_3PL}[cfg["irt_model"]]
     model = cls(cfg["ability_dim"], cfg["I"], hidden_dim=64, ability_merge=cfg.get("merge", "product"),
-                conditional_posterior=cfg["conditional"],
+                conditional_posterior=cfg["conditional"], generative_model=cfg.get("generative", "irt"),
+                response_dist=cfg.get("response_dist", "bernoulli"),
                 replace_missing_with_prior=not cfg["drop_missing"], n_norm_flows=cfg["n_flows"])
     missing, unexpected = model.load_state_dict(params, strict=True)
     return model.to(device)

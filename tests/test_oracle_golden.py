@@ -8,7 +8,7 @@ import torch
 
 from oracle import kernel_spec as KS
 from oracle import reference_port as RP
-from helpers import CASE_NAMES, GOLDEN, case_inputs, load_case, max_rel, rel_l2
+from helpers import PORT_CASE_NAMES as CASE_NAMES, GOLDEN, case_inputs, load_case, max_rel, rel_l2
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)

@@ -88,6 +88,7 @@ class FusedStep:
         m = trainer.model
         return (trainer.on_gpu and response.is_cuda and m.ability_merge == 'product'
                 and not m.conditional_posterior and m.n_norm_flows == 0 and m.hidden_dim <= 256
+                and m.generative_model == 'irt' and m.response_dist == 'bernoulli'
                 and getattr(m, "fuse_param_chain", True))
 
     def run(self, response, mask, train, eps_item=None, eps_ability=None):

@@ -16,7 +16,7 @@ ELBO_KL, ELBO_SAMPLE = K.ELBO_KL, K.ELBO_SAMPLE
 MISSING_PRIOR, MISSING_DROP = K.MISSING_PRIOR, K.MISSING_DROP
 
 
-def prepare_rows(response: torch.Tensor, mask: torch.Tensor):
+def prepare_rows(response: torch.Tensor, mask: torch.Tensor, binary: bool = True):
     """(P, I, 1) float response + any-dtype mask -> (P, I) float32 and (P, I)
     uint8 views the kernels read.  bool/uint8 masks are reinterpreted without a
     copy; the int64 mask the reference CLI builds (vibo.py:240) costs one

@@ -25,6 +25,7 @@ from torch import nn
 from torch.nn import init
 
 from . import functional as VF
+from .decoders import DeepIRT, LinkedIRT, ResidualIRT
 from .flows import NormalizingFlows, PlanarFlow
 
 LOG_SQRT_2PI = 0.5 * math.log(2.0 * math.pi)
@@ -127,12 +128,53 @@ class AbilityInferenceNetwork(nn.Module):
     def missing_policy(self):
         return VF.MISSING_PRIOR if self.replace_missing_with_prior else VF.MISSING_DROP
 
+    # continuous responses (--response-dist gaussian): a cell's MLP input is no longer one of 2
+    # values, so the expert table does not exist and the encoder runs PER CELL (reference
+    # models.py:596-629 / :631-650 literally), in person chunks so activations stay bounded
+    per_cell = False
+    per_cell_chunk = 4096
+
+    def _forward_per_cell(self, resp, msk, item_feat):
+        P, I = resp.shape
+        D = self.ability_dim
+        mus, lvs = [], []
+        for a in range(0, P, self.per_cell_chunk):
+            r = resp[a:a + self.per_cell_chunk]
+            o = msk[a:a + self.per_cell_chunk] != 0
+            n = r.shape[0]
+            flat = r.reshape(n * I, 1)
+            if self.conditional:
+                flat = torch.cat([flat, item_feat.unsqueeze(0).expand(n, I, -1).reshape(n * I, -1)], dim=1)
+            if self.ability_merge == 'mean':
+                hid = F.elu(self.mlp1(flat)).reshape(n, I, self.hidden_dim)
+                w = o.unsqueeze(2).to(hid.dtype)
+                hid_mean = (hid * w).sum(1) / w.sum(1)
+                mu, lv = torch.chunk(self.mlp2(hid_mean), 2, dim=1)
+            else:
+                out = self.mlp(flat).reshape(n, I, 2 * D)
+                mu_c, lv_c = out[:, :, :D], out[:, :, D:]
+                # product of experts (utils.py:105-113) with prior experts N(0, 1) for the missing
+                # cells, or none of them under --drop-missing (models.py:606-627)
+                T = 1.0 / (torch.exp(lv_c) + 1e-8)
+                obs = o.unsqueeze(2)
+                prior_T = 1.0 / (1.0 + 1e-8) if self.replace_missing_with_prior else 0.0
+                T = torch.where(obs, T, torch.full_like(T, prior_T))
+                mu_c = torch.where(obs, mu_c, torch.zeros_like(mu_c))
+                S = T.sum(1)
+                mu = (mu_c * T).sum(1) / S
+                lv = torch.log(1.0 / S)
+            mus.append(mu)
+            lvs.append(lv)
+        return torch.cat(mus), torch.cat(lvs)
+
     def expert_table(self, item_feat=None):
         """(2, 1, 2D): the MLP on the two possible cell inputs r = 0, 1."""
         return self.mlp(self._cell_inputs.to(self.mlp[0].weight.dtype)).unsqueeze(1)
 
     def forward(self, response, mask, item_feat=None):
         resp, msk = VF.prepare_rows(response, mask)
+        if self.per_cell:
+            return self._forward_per_cell(resp, msk, item_feat)
         if self.ability_merge == 'mean':
             return self._forward_mean(resp, msk, item_feat)
         table = self.expert_table(item_feat)
@@ -207,10 +249,6 @@ class VIBO_1PL(nn.Module):
         assert ability_merge in ['mean', 'product']
         assert generative_model in ['irt', 'link', 'deep', 'residual']
         assert response_dist in ['bernoulli', 'gaussian']
-        if generative_model != 'irt':
-            raise NotImplementedError("only generative_model='irt' runs on the B200 kernels")
-        if response_dist != 'bernoulli':
-            raise NotImplementedError("only response_dist='bernoulli' runs on the B200 kernels")
 
         self.latent_dim = latent_dim
         self.ability_dim = latent_dim
@@ -239,6 +277,14 @@ class VIBO_1PL(nn.Module):
         if n_norm_flows > 0:
             self.ability_norm_flows = NormalizingFlows(self.ability_dim, n_flows=n_norm_flows)
             self.item_norm_flows = NormalizingFlows(self.item_feat_dim, n_flows=n_norm_flows)
+        # nonlinear generative models (reference models.py:311-327, :769-919)
+        if generative_model == 'link':
+            self.decoder = LinkedIRT(irt_model=f'{self.irt_num}pl', hidden_dim=self.hidden_dim)
+        elif generative_model == 'deep':
+            self.decoder = DeepIRT(self.ability_dim, irt_model=f'{self.irt_num}pl', hidden_dim=self.hidden_dim)
+        elif generative_model == 'residual':
+            self.decoder = ResidualIRT(self.ability_dim, irt_model=f'{self.irt_num}pl', hidden_dim=self.hidden_dim)
+        self.ability_encoder.per_cell = response_dist == 'gaussian'
         self.apply(self.weights_init)
 
     # ------------------------------------------------------------------ setup
@@ -287,7 +333,33 @@ class VIBO_1PL(nn.Module):
 
     def decode(self, ability, item_feat):
         """reference models.py:373-378 -> response_mu (P, I, 1)."""
-        return VF.Decode.apply(ability, item_feat, self.irt_num)
+        if self.generative_model == 'irt':
+            return VF.Decode.apply(ability, item_feat, self.irt_num)
+        return self.decoder(ability, item_feat)
+
+    decode_chunk = 4096   # persons per decoder call in the loss paths (bounds the (P, I, H) activations)
+
+    def _loglik(self, resp, msk, ability, item_feat):
+        """sum_ij o_ij log p(x_ij | ability_i, item_feat_j) for the configured generative model and
+        response distribution (reference models.py:397-404): the fused link kernel for the IRT /
+        Bernoulli model, otherwise decoder (person chunks) + the materialised-probability kernels."""
+        if self.generative_model == 'irt' and self.response_dist == 'bernoulli':
+            return VF.LinkLogLik.apply(resp, msk, ability, item_feat, self.irt_num)
+        total = 0.0
+        for a in range(0, resp.shape[0], self.decode_chunk):
+            b = a + self.decode_chunk
+            mu = self.decode(ability[a:b], item_feat)
+            total = total + self._loglik_given_mu(resp[a:b], msk[a:b], mu)
+        return total
+
+    def _loglik_given_mu(self, resp, msk, response_mu):
+        if self.response_dist == 'bernoulli':
+            return VF.BernoulliLogLik.apply(resp, msk, response_mu)
+        # masked_gaussian_log_pdf with response_logvar = 2 log 0.1 (models.py:400-402, utils.py:52-56)
+        mu = response_mu.reshape(resp.shape)
+        sigma = 0.1
+        lp = -((resp - mu) ** 2) / (2 * sigma * sigma) - math.log(sigma) - LOG_SQRT_2PI
+        return (lp * (msk != 0).to(lp.dtype)).sum()
 
     def forward(self, response, mask):
         """reference models.py:337-354 -> 9-tuple (13-tuple with flows)."""
@@ -307,8 +379,8 @@ class VIBO_1PL(nn.Module):
              item_feat_mu, item_feat_logvar, annealing_factor=1, use_kl_divergence=True,
              ability_k=None, item_feat_k=None, ability_logabsdetjac=None, item_logabsdetjac=None):
         """reference models.py:380-443 on a materialised response_mu -> -ELBO (0-d)."""
-        resp, msk = VF.prepare_rows(response, mask)
-        ll = VF.BernoulliLogLik.apply(resp, msk, response_mu)
+        resp, msk = VF.prepare_rows(response, mask, binary=self.response_dist == 'bernoulli')
+        ll = self._loglik_given_mu(resp, msk, response_mu)
         return -self._assemble_elbo(ll, ability, ability_mu, ability_logvar, item_feat, item_feat_mu,
                                     item_feat_logvar, annealing_factor, use_kl_divergence, ability_k,
                                     item_feat_k, ability_logabsdetjac, item_logabsdetjac)
@@ -341,7 +413,8 @@ class VIBO_1PL(nn.Module):
         with torch.no_grad():
             resp, msk = VF.prepare_rows(response, mask)
             if (resp.is_cuda and self.ability_merge == 'product' and not self.conditional_posterior
-                    and self.n_norm_flows == 0):
+                    and self.n_norm_flows == 0 and self.generative_model == 'irt'
+                    and self.response_dist == 'bernoulli'):
                 if seed is None and (eps_item is None or eps_ability is None):
                     seed = int(torch.randint(0, 2 ** 62, (1,)).item())
                 item_mu, item_lv = self.item_encoder()
@@ -364,6 +437,12 @@ class VIBO_1PL(nn.Module):
         (``vibo_predictive_mean``) instead of S decodes stacked on the host."""
         with torch.no_grad():
             _, a_mu, a_lv, _, i_mu, i_lv = self.encode(response, mask)
+            if self.generative_model != 'irt':
+                acc = 0.0
+                for _ in range(num_samples):
+                    acc = acc + self.decode(a_mu + torch.exp(0.5 * a_lv) * torch.randn_like(a_mu),
+                                            i_mu + torch.exp(0.5 * i_lv) * torch.randn_like(i_mu))
+                return acc / num_samples
             if seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             out = VF.K.predictive_mean(a_mu, a_lv, i_mu, i_lv, num_samples, irt_model=self.irt_num, seed=seed)
@@ -383,7 +462,7 @@ class VIBO_1PL(nn.Module):
         item_term_scale: weight of the item-side prior term; a person-sharded
         run passes 1/world_size so that the all-reduced sum counts it once.
         """
-        resp, msk = VF.prepare_rows(response, mask)
+        resp, msk = VF.prepare_rows(response, mask, binary=self.response_dist == 'bernoulli')
         P = resp.shape[0]
         item_feat_mu, item_feat_logvar = self.item_encoder()
         host_rows = (not resp.is_cuda) and item_feat_mu.is_cuda
@@ -395,8 +474,11 @@ class VIBO_1PL(nn.Module):
         if eps_item is None:
             eps_item = torch.randn_like(item_feat_mu)
         kl_form = bool(use_kl_divergence)
+        general = self.generative_model != 'irt' or self.response_dist != 'bernoulli'
+        if general and host_rows:
+            raise NotImplementedError("host-resident rows need generative_model='irt' and Bernoulli responses")
         # unconditional model on the GPU: the whole parameter-side chain is two small kernels
-        if self.ability_merge == 'mean':
+        if self.ability_merge == 'mean' or self.ability_encoder.per_cell:
             item_feat = eps_item * torch.exp(0.5 * item_feat_logvar) + item_feat_mu
             if eps_ability is None and seed is None:
                 eps_ability = torch.randn(P, self.ability_dim, dtype=torch.float32, device=resp.device)
@@ -404,7 +486,7 @@ class VIBO_1PL(nn.Module):
                                        seed, person_offset, item_term_scale, return_outputs,
                                        float(annealing_factor), kl_form)
         chain = (self.fuse_param_chain and item_feat_mu.is_cuda and not self.conditional_posterior
-                 and self.n_norm_flows == 0 and self.hidden_dim <= 256)
+                 and self.n_norm_flows == 0 and self.hidden_dim <= 256 and not general)
         if chain:
             mlp = self.ability_encoder.mlp
             item_feat, table, item_term_raw = VF.ParamChain.apply(
@@ -418,7 +500,7 @@ class VIBO_1PL(nn.Module):
             eps_ability = torch.randn(P, self.ability_dim, dtype=torch.float32, device=resp.device)
         beta = float(annealing_factor)
 
-        if self.n_norm_flows > 0:
+        if self.n_norm_flows > 0 or general:
             return self._composed_elbo(resp, msk, table, item_feat, item_feat_mu, item_feat_logvar,
                                        eps_ability, seed, person_offset, item_term_scale, return_outputs,
                                        beta, kl_form)
@@ -461,7 +543,9 @@ class VIBO_1PL(nn.Module):
         prior terms.  Used for --n-norm-flows (reference models.py:406-424, where
         annealing_factor is ignored exactly as in the reference) and --ability-merge mean."""
         enc = self.ability_encoder
-        if self.ability_merge == 'mean':
+        if enc.per_cell:
+            a_mu, a_lv = enc._forward_per_cell(resp, msk, item_feat if self.conditional_posterior else None)
+        elif self.ability_merge == 'mean':
             a_mu, a_lv = enc._forward_mean(resp, msk, item_feat if self.conditional_posterior else None)
         else:
             a_mu, a_lv = VF.EncodePosterior.apply(resp, msk, table, enc.conditional, enc.missing_policy)
@@ -481,14 +565,14 @@ class VIBO_1PL(nn.Module):
                 ability_k, a_ldj = self.ability_norm_flows(ability)
                 person = standard_normal_log_pdf(ability_k).sum() \
                     - (normal_log_pdf(ability, a_mu, a_lv).sum() - a_ldj.sum())
-            ll = VF.LinkLogLik.apply(resp, msk, ability_k, item_k, self.irt_num)
+            ll = self._loglik(resp, msk, ability_k, item_k)
             item = standard_normal_log_pdf(item_k).sum() \
                 - (normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum() - i_ldj.sum())
             loss = -(ll + person + item_term_scale * item)
             outputs.update(ability=ability, ability_k=ability_k, item_feat_k=item_k)
         else:
             ability = eps_ability * torch.exp(0.5 * a_lv) + a_mu
-            ll = VF.LinkLogLik.apply(resp, msk, ability, item_feat, self.irt_num)
+            ll = self._loglik(resp, msk, ability, item_feat)
             if kl_form:
                 person = -beta * kl_divergence_standard_normal_prior(a_mu, a_lv).sum()
                 item = -beta * kl_divergence_standard_normal_prior(item_feat_mu, item_feat_logvar).sum()
@@ -508,4 +592,91 @@ class VIBO_2PL(VIBO_1PL):
 
 
 class VIBO_3PL(VIBO_2PL):
+    irt_num = 3
+
+
+# ---------------------------------------------------------------------------------------------
+# Un-amortized variational IRT (reference models.py:89-243): per-person posterior tables instead
+# of an inference network.  Same generative side, so the same link / log-likelihood kernel.
+# ---------------------------------------------------------------------------------------------
+class VI_1PL(nn.Module):
+    irt_num = 1
+
+    def __init__(self, latent_dim, num_person, num_item):
+        super().__init__()
+        self.latent_dim = latent_dim
+        self.ability_dim = latent_dim
+        self.response_dim = 1
+        self.num_person = num_person
+        self.num_item = num_item
+        self.item_feat_dim = {1: 1, 2: latent_dim + 1, 3: latent_dim + 2}[self.irt_num]
+        # construction order == reference (models.py:107-113): N(0, 1) embeddings, RNG-compatible
+        self.ability_mu_lookup = nn.Embedding(num_person, self.ability_dim)
+        self.ability_logvar_lookup = nn.Embedding(num_person, self.ability_dim)
+        self.item_mu_lookup = nn.Embedding(num_item, self.item_feat_dim)
+        self.item_logvar_lookup = nn.Embedding(num_item, self.item_feat_dim)
+
+    reparameterize_gaussian = staticmethod(VIBO_1PL.reparameterize_gaussian)
+
+    def encode(self, index, response, mask):
+        """reference models.py:128-143 -> 6-tuple (item draw first, then abilities)."""
+        item_feat_mu, item_feat_logvar = self.item_mu_lookup.weight, self.item_logvar_lookup.weight
+        item_feat = self.reparameterize_gaussian(item_feat_mu, item_feat_logvar)
+        idx = index.reshape(-1).long()
+        ability_mu, ability_logvar = self.ability_mu_lookup(idx), self.ability_logvar_lookup(idx)
+        ability = self.reparameterize_gaussian(ability_mu, ability_logvar)
+        return ability, ability_mu, ability_logvar, item_feat, item_feat_mu, item_feat_logvar
+
+    def decode(self, ability, item_feat):
+        return VF.Decode.apply(ability, item_feat, self.irt_num)
+
+    def forward(self, index, response, mask):
+        ability, ability_mu, ability_logvar, item_feat, item_feat_mu, item_feat_logvar = \
+            self.encode(index, response, mask)
+        return (response, mask, self.decode(ability, item_feat), ability, ability_mu, ability_logvar,
+                item_feat, item_feat_mu, item_feat_logvar)
+
+    def _terms(self, ll, ability, ability_mu, ability_logvar, item_feat, item_feat_mu, item_feat_logvar,
+               annealing_factor, use_kl_divergence):
+        if use_kl_divergence:
+            kl_u = kl_divergence_standard_normal_prior(ability_mu, ability_logvar).sum()
+            kl_d = kl_divergence_standard_normal_prior(item_feat_mu, item_feat_logvar).sum()
+            return ll - annealing_factor * kl_u - annealing_factor * kl_d
+        log_p = standard_normal_log_pdf(ability).sum() + standard_normal_log_pdf(item_feat).sum()
+        log_q = normal_log_pdf(ability, ability_mu, ability_logvar).sum() \
+            + normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum()
+        return (ll + log_p) - log_q
+
+    def elbo(self, response, mask, response_mu, ability, ability_mu, ability_logvar, item_feat,
+             item_feat_mu, item_feat_logvar, annealing_factor=1, use_kl_divergence=True):
+        """reference models.py:148-177 on a materialised response_mu -> -ELBO (0-d)."""
+        resp, msk = VF.prepare_rows(response, mask)
+        ll = VF.BernoulliLogLik.apply(resp, msk, response_mu)
+        return -self._terms(ll, ability, ability_mu, ability_logvar, item_feat, item_feat_mu, item_feat_logvar,
+                            annealing_factor, use_kl_divergence)
+
+    def fused_elbo(self, index, response, mask, annealing_factor=1, use_kl_divergence=True):
+        """forward + elbo (reference vi.py training step) without materialising response_mu: the
+        link + log-likelihood kernel (vibo_link_loglik) on the drawn abilities / item features."""
+        resp, msk = VF.prepare_rows(response, mask)
+        ability, ability_mu, ability_logvar, item_feat, item_feat_mu, item_feat_logvar = \
+            self.encode(index, response, mask)
+        ll = VF.LinkLogLik.apply(resp, msk, ability, item_feat, self.irt_num)
+        return -self._terms(ll, ability, ability_mu, ability_logvar, item_feat, item_feat_mu, item_feat_logvar,
+                            annealing_factor, use_kl_divergence)
+
+    def log_marginal(self, index, response, mask, num_samples=100):
+        """reference models.py:179-213 (which omits ``index`` in its forward call and cannot run as
+        written): logsumexp over sample-form -ELBOs - log(num_samples)."""
+        with torch.no_grad():
+            log_w = torch.stack([-self.fused_elbo(index, response, mask, use_kl_divergence=False)
+                                 for _ in range(num_samples)])
+            return torch.logsumexp(log_w, 0) - math.log(num_samples)
+
+
+class VI_2PL(VI_1PL):
+    irt_num = 2
+
+
+class VI_3PL(VI_2PL):
     irt_num = 3
