@@ -303,6 +303,23 @@ int vibo_predictive_mean(const vibo_desc* desc, const float* ability_mu, const f
                          const uint64_t* seed_state, float* out_mean, void* stream);
 
 /*
+ * Per-cell MLP of the nonlinear generative models (--generative-model link | deep | residual;
+ * LinkedIRT / DeepIRT / ResidualIRT, models.py:769-919) on the tcgen05 tensor cores: for every
+ * cell (person i, item j)
+ *     out_ij = w4 . ELU( W2 ELU( u_j + v_i + z_ij w0 ) + c2 ) + c4,        hidden_dim = 64
+ * u (u_rows, 64) with u_rows = num_item or 1 (one row broadcast to every item), v (v_rows, 64)
+ * likewise per person, z (P, I) with w0 (64) or both NULL; W2 (64, 64) row-major [out][in]
+ * (nn.Linear.weight), c2, w4 (64); out (P, I).  link: u = link.0.bias, z = the IRT logit,
+ * w0 = link.0.weight[:, 0]; deep / residual: u = mlp_concat.0 on the item half (+ bias),
+ * v = mlp_concat.0 on the ability half.  The hidden activations are carried as bf16 hi + lo pairs
+ * (three tcgen05.mma products, fp32 accumulation in TMEM): relative error ~1e-5.  Forward only
+ * (evaluation / predictive sampling); training differentiates through the same math in PyTorch.
+ */
+int vibo_percell_mlp(int64_t num_person, int num_item, int hidden_dim, int u_rows, int v_rows, const float* u,
+                     const float* v, const float* z, const float* w0, const float* w2, const float* c2,
+                     const float* w4, float c4, float* out, void* stream);
+
+/*
  * Planar normalizing flows on the abilities (--n-norm-flows K), per person and
  * fused with the reparameterised draw and the person-side terms of the flow
  * form of the ELBO [flows.py:21-41, :58-66; models.py:342-348, :406-424]:

@@ -59,6 +59,8 @@ SIGNATURES = {
     "vibo_bernoulli_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_param_forward": (C.c_int, [_PD, C.c_int] + [_p] * 14),
     "vibo_param_backward": (C.c_int, [_PD, C.c_int] + [_p] * 18),
+    "vibo_percell_mlp": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p,
+                                   C.c_float, _p, _p]),
     "vibo_log_marginal_workspace_bytes": (C.c_size_t, [C.c_int]),
     "vibo_log_marginal": (C.c_int, [_PD, _p, _p, _p, _p, _p, C.c_int, _p, _p, C.c_uint64, _p, _p, _p, _p,
                                     C.c_size_t, _p]),

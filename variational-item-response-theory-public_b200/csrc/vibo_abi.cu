@@ -412,6 +412,24 @@ int vibo_param_forward(const vibo_desc* desc, int hidden_dim, const float* mu_lo
   return VIBO_OK;
 }
 
+int vibo_percell_mlp(int64_t num_person, int num_item, int hidden_dim, int u_rows, int v_rows, const float* u,
+                     const float* v, const float* z, const float* w0, const float* w2, const float* c2,
+                     const float* w4, float c4, float* out, void* stream) {
+  if (num_person < 0 || num_item <= 0) return fail(VIBO_ERR_BAD_ARGUMENT, "num_person must be >= 0 and num_item > 0");
+  if (hidden_dim != 64) return fail(VIBO_ERR_UNSUPPORTED, "vibo_percell_mlp is built for hidden_dim 64");
+  if ((u_rows != 1 && u_rows != num_item) || (v_rows != 1 && v_rows != num_person))
+    return fail(VIBO_ERR_BAD_ARGUMENT, "u_rows must be 1 or num_item, v_rows 1 or num_person");
+  if (!u || !v || !w2 || !c2 || !w4 || !out || ((z == nullptr) != (w0 == nullptr)))
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer (z and w0 come together)");
+  if ((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(VIBO_ERR_MISALIGNED, "u and v must be 16-byte aligned");
+  if (num_person == 0) return VIBO_OK;
+  VIBO_CUDA(vibo::launch_percell_mlp(num_person, num_item, u_rows, v_rows, u, v, z, w0, w2, c2, w4, c4, out,
+                                     static_cast<cudaStream_t>(stream)),
+            "percell_mlp");
+  return VIBO_OK;
+}
+
 size_t vibo_log_marginal_workspace_bytes(int num_samples) {
   return num_samples > 0 ? vibo::log_marginal_workspace_bytes(num_samples) : 0;
 }

@@ -96,6 +96,11 @@ cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const fl
                                   float* g_mu, float* g_lv, float* g_w0, float* g_b0, float* g_w2,
                                   float* g_b2, float* g_w4, float* g_b4, cudaStream_t st);
 
+// vibo_percell.cu: per-cell MLP of the nonlinear generative models on tcgen05 / TMEM (hidden width 64)
+cudaError_t launch_percell_mlp(int64_t P, int I, int u_rows, int v_rows, const float* U, const float* V,
+                               const float* Z, const float* w0, const float* W2, const float* c2, const float* w4,
+                               float c4, float* out, cudaStream_t st);
+
 // vibo_pack.cu: one-byte-per-cell row format
 cudaError_t launch_pack(int64_t n, const float* resp, const uint8_t* mask, int8_t* out, cudaStream_t st);
 cudaError_t launch_unpack(int64_t n, const int8_t* in, float* resp, uint8_t* mask, cudaStream_t st);

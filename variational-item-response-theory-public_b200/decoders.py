@@ -50,6 +50,34 @@ def percell_tail(pre1, lin2, lin3):
     return F.linear(h, lin3.weight, lin3.bias)
 
 
+def use_tensor_core_kernel(lin2, *tensors):
+    """The tcgen05 kernel serves the no-gradient paths (evaluation, log-marginal, predictive
+    sampling) on the GPU at hidden width 64; with autograd active the same math runs in PyTorch."""
+    import os
+    if os.environ.get("VIBO_DISABLE_TCGEN05") == "1":
+        return False
+    if not lin2.weight.is_cuda or lin2.weight.shape != (64, 64) or lin2.weight.dtype != torch.float32:
+        return False
+    if torch.is_grad_enabled() and (lin2.weight.requires_grad or any(t is not None and t.requires_grad
+                                                                     for t in tensors)):
+        return False
+    return True
+
+
+def percell(u, v, z, lin1_w0, lin2, lin3):
+    """out (P, I, 1) = lin3(ELU(lin2(ELU(u_j + v_i + z_ij w0)))): the per-cell MLP every nonlinear
+    decoder reduces to.  u (I or 1, H), v (P or 1, H), z (P, I, 1) / w0 (H) or None."""
+    if use_tensor_core_kernel(lin2, u, v, z):
+        from . import kernels as K
+        out = K.percell_mlp(u, v, None if z is None else z[:, :, 0], lin1_w0, lin2.weight, lin2.bias,
+                            lin3.weight[0])
+        return (out + lin3.bias).unsqueeze(2)
+    pre1 = v[:, None, :] + u[None, :, :]
+    if z is not None:
+        pre1 = pre1 + z * lin1_w0
+    return percell_tail(pre1, lin2, lin3)
+
+
 class LinkedIRT(nn.Module):
     """sigmoid(MLP(irt logit)) (reference models.py:769-808)."""
 
@@ -69,8 +97,9 @@ class LinkedIRT(nn.Module):
     def forward(self, ability, item_feat):
         logit, guess = irt_logit(ability, item_feat, self.irt_num)
         lin1, lin2, lin3 = self.link[0], self.link[2], self.link[4]
-        pre1 = logit * lin1.weight[:, 0] + lin1.bias          # (P, I, H): w0 z + c0
-        prob = torch.sigmoid(percell_tail(pre1, lin2, lin3))
+        zero = torch.zeros(1, self.hidden_dim, dtype=logit.dtype, device=logit.device)
+        # a1 = w0 z + c0: u = the bias row (broadcast over items), no per-person term
+        prob = torch.sigmoid(percell(lin1.bias[None, :], zero, logit, lin1.weight[:, 0], lin2, lin3))
         if guess is not None:
             g = guess[None, :, None]
             return g + (1. - g) * prob
@@ -107,7 +136,7 @@ class DeepIRT(nn.Module):
         # cat([hid_item_j, hid_ability_i]) @ W1.T + c1, without the (P, I, 2H) tensor
         u = F.linear(hid_item, lin1.weight[:, :H], lin1.bias)      # (I, H)
         v = F.linear(hid_ability, lin1.weight[:, H:])              # (P, H)
-        return percell_tail(v[:, None, :] + u[None, :, :], lin2, lin3)   # (P, I, 1)
+        return percell(u, v, None, None, lin2, lin3)   # (P, I, 1)
 
     def forward(self, ability, item_feat):
         return torch.sigmoid(self.residual_forward(ability, item_feat))

@@ -410,3 +410,26 @@ def pack_rows_host(response, mask):
     m = mask.reshape(mask.shape[0], mask.shape[1]) != 0
     out = torch.where(m, (r > 0.5).to(torch.int8), torch.full((), -1, dtype=torch.int8))
     return out.contiguous().pin_memory() if torch.cuda.is_available() else out.contiguous()
+
+
+def percell_mlp(u, v, z, w0, w2, c2, w4, c4=0.0):
+    """vibo_percell_mlp -> (P, I) float32: w4 . ELU(W2 ELU(u_j + v_i + z_ij w0) + c2) + c4 on the tcgen05
+    tensor cores.  u (I or 1, 64), v (P or 1, 64), z (P, I) with w0 (64) or both None; P and I are taken
+    from z, else from v and u."""
+    if not w2.is_cuda:
+        raise _lib.ViboError("VIBO kernels need CUDA tensors (no CPU fallback exists)")
+    H = w2.shape[0]
+    u, v = u.contiguous().float(), v.contiguous().float()
+    if z is not None:
+        z = z.contiguous().float()
+        P, I = z.shape
+    else:
+        P, I = v.shape[0], u.shape[0]
+    out = torch.empty(P, I, dtype=torch.float32, device=w2.device)
+    rc = _lib.load().vibo_percell_mlp(P, I, H, u.shape[0], v.shape[0], _ptr(u), _ptr(v), _ptr(z),
+                                      _ptr(None if w0 is None else w0.contiguous().float()),
+                                      _ptr(w2.contiguous().float()), _ptr(c2.contiguous().float()),
+                                      _ptr(w4.contiguous().float()), C.c_float(float(c4)), _ptr(out),
+                                      _stream(w2.device))
+    _lib.check(rc, "vibo_percell_mlp")
+    return out
