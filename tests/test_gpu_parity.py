@@ -86,17 +86,27 @@ GRID = [
     (40, 17, 2, 1, True, 0.0, 0, 0),
     (45, 640, 7, 3, True, 0.05, 1, 1),
     (64, 2000, 3, 2, True, 0.1, 0, 0),
+    # tcgen05 conditional encode: several 128-person tiles per CTA-less grid, ragged last tile, exact K
+    # blocks (I % 32 == 0) and a zero-filled tail block, missing cells (row-level exact fallback)
+    (1000, 1000, 5, 3, True, 0.0, 0, 0),
+    (300, 512, 4, 2, True, 0.02, 0, 0),
+    (129, 36, 1, 1, True, 0.0, 0, 0),
+    (257, 100, 2, 3, True, 0.3, 1, 1),
     (64, 1500, 2, 3, False, 0.2, 0, 0),
 ]
 
 
 # which implementation serves the call:
 #   fused    - single-pass kernel where it applies, else the composition below
-#   composed - three passes: tensor-core (mma.sync) encode / encode-backward for a conditional
-#              posterior, slab-stream kernels otherwise
+#   composed - three passes: tensor-core encode (tcgen05 / TMEM / 2-D TMA where D <= 5 and I % 4 == 0,
+#              else mma.sync) and mma.sync encode-backward for a conditional posterior, slab-stream
+#              kernels otherwise
+#   mma      - the same with the tcgen05 encode disabled (VIBO_DISABLE_TC5=1)
 #   slab     - three passes, slab-stream kernels only (VIBO_DISABLE_MMA=1)
 #   legacy   - three passes, the original row-slab kernels (unaligned-pointer fallback)
 PATHS = {"fused": {}, "composed": {"VIBO_DISABLE_FUSED": "1"},
+         # conditional encode on mma.sync instead of the tcgen05 / TMA kernel
+         "mma": {"VIBO_DISABLE_FUSED": "1", "VIBO_DISABLE_TC5": "1"},
          "slab": {"VIBO_DISABLE_FUSED": "1", "VIBO_DISABLE_MMA": "1"},
          "legacy": {"VIBO_DISABLE_FUSED": "1", "VIBO_DISABLE_MMA": "1", "VIBO_DISABLE_STREAM": "1"}}
 

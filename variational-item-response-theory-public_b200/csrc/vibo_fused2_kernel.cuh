@@ -287,8 +287,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
   const FusedSmem L = fused_smem_layout(I, D, MODEL, R, NS, NQ, f2_scratch_bytes(R, NS, D));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);   // [NQ * NS] (<= 16)
   int* done_cnt = reinterpret_cast<int*>(smem + 128);
-  float* s_max = reinterpret_cast<float*>(smem + 256);      // amax[0..7], bmax, sum a'[0..1], sum b'
-  double* s_wsum = reinterpret_cast<double*>(smem + 256 + kF2SumOff);   // [warp][3] setup partials
+  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + 256);   // [NQ * NS]: every warp of a team arrives when it leaves the stage
+  float* s_max = reinterpret_cast<float*>(smem + kFusedHdr);      // amax[0..7], bmax, sum a'[0..1], sum b'
+  double* s_wsum = reinterpret_cast<double*>(smem + kFusedHdr + kF2SumOff);   // [warp][3] setup partials
   float* s_param = reinterpret_cast<float*>(smem + L.params_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -298,14 +299,16 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
   const int64_t chunk0 = (int64_t)blockIdx.x * NQ + team, chunk_step = (int64_t)gridDim.x * NQ;
   uint64_t* t_full = full_bar + team * NS;
   int* t_done = done_cnt + team * NS;
+  uint64_t* t_empty = empty_bar + team * NS;
   unsigned char* t_stage = smem + L.stage_off + (size_t)team * NS * L.stage_bytes;
   static_assert(D <= 2, "setup sums / phase B are sized for D <= 2");
-  float* t_theta = reinterpret_cast<float*>(smem + 256 + kF2ThetaOff) + (size_t)team * NS * R * D * 2;
+  float* t_theta = reinterpret_cast<float*>(smem + kFusedHdr + kF2ThetaOff) + (size_t)team * NS * R * D * 2;
 
   // ---- one-time setup ----------------------------------------------------
   if (threadIdx.x == 0) {
     for (int s = 0; s < NQ * NS; ++s) {
       mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], TW);
       done_cnt[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -621,6 +624,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
     __syncwarp();
     int last = 0;
     if (lane == 0) {
+      // release: this warp's reads of the stage are complete (mbarrier arrive); the counter only
+      // ELECTS the warp that arrived last, which then acquires the completed 'empty' phase before
+      // it lets the bulk copy overwrite the stage
+      mbar_arrive(&t_empty[s]);
       __threadfence_block();
       last = atomicAdd(&t_done[s], 1) == TW - 1;
       if (last) atomicExch(&t_done[s], 0);
@@ -628,6 +635,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last && it + NS < n_it) {
       const int64_t cn = chunk0 + (int64_t)(it + NS) * chunk_step;
+      mbar_wait(&t_empty[s], phase);
       fused_issue_chunk<D>(p, L, cn, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
     }
     if (++s == NS) {

@@ -130,6 +130,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+constexpr int kFusedHdr = 512;
 __host__ __device__ inline size_t fused_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Shared-memory layout (bytes): barriers | item params (SoA floats) | stages.
@@ -140,7 +141,9 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int I, int D, int model, 
                                                        int nteams = kFusedTeams, int scratch_bytes = 0) {
   FusedSmem L;
   const int nparam = model == 1 ? 1 : (model == 2 ? D + 1 : D + 2);
-  L.params_off = 256 + scratch_bytes;  // [0,128): up to 16 mbarriers; [128,192): up to 16 stage counters
+  // header: [0,128) up to 16 'full' mbarriers; [128,192) up to 16 stage counters; [256,384) up to 16
+  // 'empty' mbarriers; scratch from kFusedHdr
+  L.params_off = kFusedHdr + scratch_bytes;
   L.stage_off = fused_align(L.params_off + (size_t)nparam * I * 4, 128);
   L.resp_bytes = (size_t)R * I * 4;
   L.mask_off = L.resp_bytes;
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
   constexpr int TW = kFusedTeamWarps, NQ = kFusedTeams;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);     // [NQ * NS]
   int* done_cnt = reinterpret_cast<int*>(smem + 128);          // warps finished with each stage
+  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + 256);   // [NQ * NS]: every warp of a team arrives when it leaves the stage
   float* s_param = reinterpret_cast<float*>(smem + L.params_off);  // [a_0 | .. | a_{D-1} | b | guess]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -354,12 +358,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
   const int64_t chunk0 = (int64_t)blockIdx.x * NQ + team, chunk_step = (int64_t)gridDim.x * NQ;
   uint64_t* t_full = full_bar + team * NS;
   int* t_done = done_cnt + team * NS;
+  uint64_t* t_empty = empty_bar + team * NS;
   unsigned char* t_stage = smem + L.stage_off + (size_t)team * NS * L.stage_bytes;
 
   // ---- one-time setup ----------------------------------------------------
   if (threadIdx.x == 0) {
     for (int s = 0; s < NQ * NS; ++s) {
       mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], TW);
       done_cnt[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -569,6 +575,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
       __syncwarp();
       int last = 0;
       if (lane == 0) {
+        // release: this warp's reads of the stage are complete (mbarrier arrive); the counter only
+        // ELECTS the warp that arrived last, which then acquires the completed 'empty' phase before
+        // it lets the bulk copy overwrite the stage
+        mbar_arrive(&t_empty[s]);
         __threadfence_block();
         last = atomicAdd(&t_done[s], 1) == TW - 1;
         if (last) atomicExch(&t_done[s], 0);
@@ -576,7 +586,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
       last = __shfl_sync(0xffffffffu, last, 0);
       if (last && p.debug != 2) {
         const int64_t cn = c + (int64_t)NS * chunk_step;
-        if (cn < n_chunks) fused_issue_chunk<D>(p, L, cn, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
+        if (cn < n_chunks) {
+          mbar_wait(&t_empty[s], phase);
+          fused_issue_chunk<D>(p, L, cn, t_stage + (size_t)s * L.stage_bytes, &t_full[s], lane);
+        }
       }
       if (p.debug != 2) {
         if (++s == NS) {

@@ -96,6 +96,10 @@ cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const fl
                                   float* g_mu, float* g_lv, float* g_w0, float* g_b0, float* g_w2,
                                   float* g_b2, float* g_w4, float* g_b4, cudaStream_t st);
 
+// vibo_tc5_encode.cu: conditional encode on tcgen05 (TF32, 2-D TMA, TMEM accumulators)
+cudaError_t tc5_encode(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table, float* mu,
+                       float* lv, float* S, cudaStream_t st);
+
 // vibo_percell.cu: per-cell MLP of the nonlinear generative models on tcgen05 / TMEM (hidden width 64)
 cudaError_t launch_percell_mlp(int64_t P, int I, int u_rows, int v_rows, const float* U, const float* V,
                                const float* Z, const float* w0, const float* W2, const float* c2, const float* w4,

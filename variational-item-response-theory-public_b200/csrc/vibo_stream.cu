@@ -276,6 +276,14 @@ cudaError_t run_encode_bwd(const vibo_desc& d, const StreamPlan& pl, const Strea
 cudaError_t stream_encode(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table,
                           float* mu, float* lv, float* S, int* grid_out, cudaStream_t st) {
   if (!aligned16(resp) || !aligned16(mask)) return cudaErrorNotSupported;
+  {
+    // conditional posterior, D <= 5, I % 4 == 0: tcgen05 / TMA streaming kernel (vibo_tc5_encode.cu)
+    const cudaError_t e5 = tc5_encode(d, resp, mask, table, mu, lv, S, st);
+    if (e5 != cudaErrorNotSupported) {
+      if (grid_out) *grid_out = sm_count();
+      return e5;
+    }
+  }
   const MmaPlan mp = mma_plan(d);
   if (mp.ok) {
     StreamPlan sp;
