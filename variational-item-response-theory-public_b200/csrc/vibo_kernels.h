@@ -100,6 +100,10 @@ cudaError_t launch_param_backward(int I, int F, int D, int H, int form, const fl
 cudaError_t tc5_encode(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table, float* mu,
                        float* lv, float* S, cudaStream_t st);
 
+cudaError_t tc5_encode_bwd(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* amu,
+                           const float* S, const float* g_mu, const float* g_lv, float* part, int* grid_out,
+                           cudaStream_t st);
+
 // vibo_percell.cu: per-cell MLP of the nonlinear generative models on tcgen05 / TMEM (hidden width 64)
 cudaError_t launch_percell_mlp(int64_t P, int I, int u_rows, int v_rows, const float* U, const float* V,
                                const float* Z, const float* w0, const float* W2, const float* c2, const float* w4,

@@ -359,6 +359,11 @@ cudaError_t stream_encode_bwd(const vibo_desc& d, const float* resp, const uint8
   if (!aligned16(resp) || !aligned16(mask) || !aligned16(amu) || !aligned16(S) || !aligned16(g_mu) ||
       !aligned16(g_lv))
     return cudaErrorNotSupported;
+  {
+    // conditional posterior, D <= 5, I % 4 == 0: tcgen05 / TMA kernel (vibo_tc5_encode_bwd.cu)
+    const cudaError_t e5 = tc5_encode_bwd(d, resp, mask, amu, S, g_mu, g_lv, part, grid_out, st);
+    if (e5 != cudaErrorNotSupported) return e5;
+  }
   const float* parr[4] = {amu, S, g_mu, g_lv};
   const BwdMmaPlan mp = bwd_mma_plan(d);
   if (mp.ok) {
