@@ -9,8 +9,9 @@
 //   * A operand = X^T: the same 2-D TMA boxes of the float32 response matrix as the forward kernel
 //     (32 items x 32 persons, 128-byte swizzle with 32-byte atoms); the rows of a box are persons = the K dimension, so
 //     the box IS the UMMA canonical MN-major layout (no transposition pass), exact in TF32;
-//   * B operand = [GN | GS] of 32 persons, computed per chunk by the CUDA cores, split into three TF32
-//     terms (6D <= 30 columns), written K-major / swizzled;
+//   * B operand = [GN | GS], computed by the CUDA cores for 128 persons at a time (four 32-person K
+//     blocks; one pass hides its global-memory latency behind ~13 us of streaming), split into three
+//     TF32 terms (6D <= 30 columns), written K-major / swizzled, double buffered;
 //   * D = 8 item tiles x (128 items x 32 columns) fp32 accumulators resident in TMEM (256 columns) for
 //     the WHOLE kernel: tcgen05.mma.kind::tf32 (M = 128 items, N = 32, K = 8 persons), one thread
 //     issues; a CTA walks its person chunks once and emits one partial at the end.
@@ -30,6 +31,7 @@ namespace vibo {
 namespace {
 
 constexpr int kB5Items = 128, kB5KP = 32, kB5N = 32, kB5Stages = 6, kB5Threads = 192;
+constexpr int kB5SP = 128, kB5Sub = kB5SP / kB5KP;   // persons per builder pass ("super-chunk") = 4 TMA / MMA chunks of 32
 constexpr uint32_t kB5BoxBytes = 32 * kB5KP * 4;          // 32 items x 32 persons: 4 KB
 constexpr uint32_t kB5StageBytes = 4 * kB5BoxBytes;       // 128 items x 32 persons: 16 KB
 constexpr uint32_t kB5BTile = kB5N * kB5KP * 4;           // 4 KB
@@ -47,13 +49,13 @@ struct B5Params {
   float* part;   // [grid][2][I][2D]
 };
 
-// shared memory (bytes): stages | B tiles (2) | G staging [32][2D] | Gsum [2D] | flags [32] | barriers
+// shared memory (bytes): stages | B tiles (2 x 4) | G staging [128][2D] | Gsum [2D] | flags [128] | barriers
 constexpr uint32_t kB5OffStage = 0;
 constexpr uint32_t kB5OffB = kB5Stages * kB5StageBytes;
-constexpr uint32_t kB5OffG = kB5OffB + 2 * kB5BTile;
-constexpr uint32_t kB5OffSum = kB5OffG + kB5KP * 2 * VIBO_MAX_ABILITY_DIM * 4;
+constexpr uint32_t kB5OffG = kB5OffB + 2 * kB5Sub * kB5BTile;
+constexpr uint32_t kB5OffSum = kB5OffG + kB5SP * 2 * 5 * 4;   // D <= 5
 constexpr uint32_t kB5OffFlag = kB5OffSum + 2 * VIBO_MAX_ABILITY_DIM * 4;
-constexpr uint32_t kB5OffBar = kB5OffFlag + 64;
+constexpr uint32_t kB5OffBar = kB5OffFlag + kB5SP;
 constexpr uint32_t kB5Smem = kB5OffBar + 8 * (2 * kB5Stages + 5) + 16;
 
 __device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,7 +158,7 @@ tc5_encode_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // B tiles: zero once (rows n >= 6D stay zero); the partial of this CTA starts at zero (exact rows add into it)
-  for (uint32_t k = t; k < 2 * kB5BTile / 16; k += kB5Threads)
+  for (uint32_t k = t; k < 2 * kB5Sub * kB5BTile / 16; k += kB5Threads)
     reinterpret_cast<uint4*>(smem + kB5OffB)[k] = make_uint4(0, 0, 0, 0);
   for (int k = t; k < 2 * I * D2; k += kB5Threads) my_part[k] = 0.0f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -164,7 +166,7 @@ tc5_encode_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *s_tmem;
-  const int64_t n_chunks = (p.P + kB5KP - 1) / kB5KP;
+  const int64_t n_chunks = (p.P + kB5SP - 1) / kB5SP;   // super-chunks of 128 persons
 
   if (warp == 0) {
     // ===================== TMA producer ===================================================
@@ -172,16 +174,21 @@ tc5_encode_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
       int s = 0;
       uint32_t ph = 0;
       for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        for (int it = 0; it < p.n_it; ++it) {
-          bar_wait(empty(s), ph ^ 1u);
-          bar_expect_tx(full(s), kB5StageBytes);
-          const uint32_t dst = st_base + (uint32_t)s * kB5StageBytes;
+        const int64_t left = p.P - c * kB5SP;
+        const int n_sub = left >= kB5SP ? kB5Sub : (int)((left + kB5KP - 1) / kB5KP);
+        for (int sub = 0; sub < n_sub; ++sub) {
+          for (int it = 0; it < p.n_it; ++it) {
+            bar_wait(empty(s), ph ^ 1u);
+            bar_expect_tx(full(s), kB5StageBytes);
+            const uint32_t dst = st_base + (uint32_t)s * kB5StageBytes;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            tma_load_2d(dst + q * kB5BoxBytes, &tmap, full(s), it * kB5Items + q * 32, (int)(c * kB5KP));
-          if (++s == kB5Stages) {
-            s = 0;
-            ph ^= 1u;
+            for (int q = 0; q < 4; ++q)
+              tma_load_2d(dst + q * kB5BoxBytes, &tmap, full(s), it * kB5Items + q * 32,
+                          (int)(c * kB5SP + sub * kB5KP));
+            if (++s == kB5Stages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
         }
       }
@@ -192,24 +199,29 @@ tc5_encode_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t ph = 0, bph = 0;
     bool first = true;
     for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+      const int64_t left = p.P - c * kB5SP;
+      const int n_sub = left >= kB5SP ? kB5Sub : (int)((left + kB5KP - 1) / kB5KP);
       bar_wait(b_full(bb), bph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int it = 0; it < p.n_it; ++it) {
-        bar_wait(full(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          const uint32_t a = st_base + (uint32_t)s * kB5StageBytes, b = b_base + (uint32_t)bb * kB5BTile;
+      for (int sub = 0; sub < n_sub; ++sub) {
+        for (int it = 0; it < p.n_it; ++it) {
+          bar_wait(full(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t a = st_base + (uint32_t)s * kB5StageBytes;
+            const uint32_t b = b_base + (uint32_t)(bb * kB5Sub + sub) * kB5BTile;
 #pragma unroll
-          for (int ks = 0; ks < kB5KP / 8; ++ks)   // 8 persons per instruction: one 1024-byte swizzle atom of A
-            umma_tf32(tmem + (uint32_t)it * kB5N, desc_mn_sw128(a + ks * 1024), desc_k_sw128(b + ks * 32),
-                      (first && ks == 0) ? 0u : 1u);
-          umma_commit(empty(s));
-          if (it == p.n_it - 1) umma_commit(b_empty(bb));
-        }
-        __syncwarp();
-        if (++s == kB5Stages) {
-          s = 0;
-          ph ^= 1u;
+            for (int ks = 0; ks < kB5KP / 8; ++ks)   // 8 persons per instruction: two 512-byte swizzle atoms of A
+              umma_tf32(tmem + (uint32_t)it * kB5N, desc_mn_sw128(a + ks * 1024), desc_k_sw128(b + ks * 32),
+                        (first && sub == 0 && ks == 0) ? 0u : 1u);
+            umma_commit(empty(s));
+            if (sub == n_sub - 1 && it == p.n_it - 1) umma_commit(b_empty(bb));
+          }
+          __syncwarp();
+          if (++s == kB5Stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
       first = false;
@@ -225,9 +237,9 @@ tc5_encode_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
     uint32_t bph = 0;
     double gsum = 0.0;      // threads e < 2D: column sum of G over this CTA's unflagged persons
     for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-      const int64_t row0 = c * kB5KP;
-      const int rows = (int)((p.P - row0 < kB5KP) ? p.P - row0 : kB5KP);
-      if (e < kB5KP) s_flag[e] = 0;
+      const int64_t row0 = c * kB5SP;
+      const int rows = (int)((p.P - row0 < kB5SP) ? p.P - row0 : kB5SP);
+      s_flag[e] = 0;
       asm volatile("bar.sync 2, 128;" ::: "memory");
       {   // persons with a missing cell (contiguous mask block of the chunk)
         const uint8_t* mb = p.mask + row0 * I;
@@ -259,14 +271,15 @@ tc5_encode_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
           if (mb[k] == 0) s_flag[k / I] = 1;
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
-      // G of the chunk: thread (person k = e / 4, columns cc = e % 4, + 4, ...)
-      bar_wait(b_empty(bb), bph ^ 1u);   // the MMAs of two chunks ago are done with this B tile
+      // G of the super-chunk: one thread per person
+      bar_wait(b_empty(bb), bph ^ 1u);   // the MMAs of two super-chunks ago are done with these B tiles
       {
-        const int k = e >> 2;
+        const int k = e;
         const int64_t row = row0 + k;
         const bool live = k < rows;
         const bool flagged = live && s_flag[k] != 0;
-        for (int cc = e & 3; cc < D2; cc += 4) {
+        const int sub = k >> 5, kk = k & 31;
+        for (int cc = 0; cc < D2; ++cc) {
           const int d = cc < D ? cc : cc - D;
           float g = 0.0f;
           if (live) {
@@ -280,8 +293,8 @@ tc5_encode_bwd_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_con
 #pragma unroll
           for (int s3 = 0; s3 < 3; ++s3) {
             const int n = s3 * D2 + cc;
-            const uint32_t off = (uint32_t)bb * kB5BTile + (uint32_t)n * 128u +
-                                 ((((uint32_t)k >> 2) ^ ((uint32_t)n & 7u)) << 4) + ((uint32_t)k & 3u) * 4u;
+            const uint32_t off = (uint32_t)(bb * kB5Sub + sub) * kB5BTile + (uint32_t)n * 128u +
+                                 ((((uint32_t)kk >> 2) ^ ((uint32_t)n & 7u)) << 4) + ((uint32_t)kk & 3u) * 4u;
             *reinterpret_cast<float*>(smem + kB5OffB + off) = parts[s3];
           }
         }
@@ -390,7 +403,7 @@ cudaError_t tc5_encode_bwd(const vibo_desc& d, const float* resp, const uint8_t*
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return cudaErrorNotSupported;
-  const int64_t n_chunks = (d.num_person + kB5KP - 1) / kB5KP;
+  const int64_t n_chunks = (d.num_person + kB5SP - 1) / kB5SP;
   int grid = sm_count();
   if ((int64_t)grid > n_chunks) grid = (int)n_chunks;
   cudaError_t e = cudaFuncSetAttribute(tc5_encode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB5Smem);
