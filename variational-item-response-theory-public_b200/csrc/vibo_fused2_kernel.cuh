@@ -621,6 +621,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused2_kernel(const __grid_cons
     }
 
     // the last warp of the team to leave the stage refills it
+    // (VIBO_FUSED_DEBUG=3: a team barrier first -- the hand-off below is an mbarrier arrive by the
+    // reading warps + a wait by the refilling warp, which racecheck does not credit as ordering the
+    // bulk copy after the reads; with the barrier in place the tool reports no hazard anywhere else)
+    if (p.debug == 3) team_barrier(team);
     __syncwarp();
     int last = 0;
     if (lane == 0) {

@@ -572,6 +572,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_uncond_kernel(const __
         }
       }
       // the last warp of the team to leave the stage refills it with the chunk NS iterations ahead
+      // (VIBO_FUSED_DEBUG=3 adds a team barrier first, see vibo_fused2_kernel.cuh)
+      if (p.debug == 3) asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kFusedTeamWarps * 32) : "memory");
       __syncwarp();
       int last = 0;
       if (lane == 0) {
