@@ -459,3 +459,41 @@ def test_packed_rows_roundtrip_and_host_entry(vb):
         c = model.fused_elbo(pk.cpu(), None, eps_item=e_i, eps_ability=e_a)
     assert float(a) == float(b)
     assert abs(float(a) - float(c)) <= 1e-6 * abs(float(a))
+
+
+@pytest.mark.parametrize("single_pass", [True, False], ids=["tc5_eval", "composed"])
+@pytest.mark.parametrize("P,I,D,irt,cond,missing,policy,form",
+                         [g for g in GRID if g[4]] + [(1000, 1000, 5, 3, True, 0.0, 0, 1), (700, 512, 1, 1, True, 0.01, 1, 0),
+                                                     (5000, 96, 2, 2, True, 0.0, 0, 0)])
+def test_forward_only_conditional_vs_oracle(vb, monkeypatch, P, I, D, irt, cond, missing, policy, form, single_pass):
+    """Forward-only vibo_fused_elbo of the conditional posterior: the single-pass tcgen05 kernel
+    (encode + on-chip link) and the two-pass composition against the fp64 oracle."""
+    if not single_pass:
+        monkeypatch.setenv("VIBO_DISABLE_TC5_EVAL", "1")
+    resp, mask, table, item, eps = _synth(P, I, D, irt, cond, missing, seed=P * 3 + I)
+    dev = "cuda"
+    out = vb.kernels.fused_elbo(torch.from_numpy(resp).to(dev), torch.from_numpy(mask).to(dev),
+                                torch.from_numpy(table).to(dev), torch.from_numpy(item).to(dev),
+                                torch.from_numpy(eps).to(dev), irt_model=irt, conditional=cond,
+                                missing_policy=policy, elbo_form=form, beta=0.7, want_grads=False,
+                                want_person_outputs=True)
+    torch.cuda.synchronize()
+    ref = KS.fused_elbo(resp.astype(np.float64), mask, table.astype(np.float64), item.astype(np.float64),
+                        eps.astype(np.float64), irt_model=irt, beta=0.7, missing_policy=policy, elbo_form=form,
+                        want_grads=False)
+    got = out["scalars"].cpu().numpy()
+    assert abs(got[0] - ref["ll"]) <= TOL * abs(ref["ll"]), (got[0], ref["ll"])
+    assert abs(got[1] - ref["person_term"]) <= TOL * max(abs(ref["person_term"]), 1.0)
+    for k in ("ability_mu", "ability_logvar", "ability"):
+        assert max_rel(out[k].cpu().numpy(), ref[k]) < TOL, k
+    # in-kernel noise: same stream as the other paths
+    a = vb.kernels.fused_elbo(torch.from_numpy(resp).to(dev), torch.from_numpy(mask).to(dev),
+                              torch.from_numpy(table).to(dev), torch.from_numpy(item).to(dev), None,
+                              irt_model=irt, conditional=cond, missing_policy=policy, elbo_form=form, seed=77,
+                              person_offset=123, want_grads=False)["scalars"].cpu().numpy()
+    e2 = vb.kernels.philox_normal(P, D, 77, 123, dev)
+    b = vb.kernels.fused_elbo(torch.from_numpy(resp).to(dev), torch.from_numpy(mask).to(dev),
+                              torch.from_numpy(table).to(dev), torch.from_numpy(item).to(dev), e2,
+                              irt_model=irt, conditional=cond, missing_policy=policy, elbo_form=form,
+                              want_grads=False)["scalars"].cpu().numpy()
+    assert np.allclose(a, b, rtol=1e-6)

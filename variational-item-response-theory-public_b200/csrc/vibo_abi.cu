@@ -154,8 +154,18 @@ static int fused_elbo_impl(const vibo_desc* desc, const float* response, const u
   }
   if (int rc = check_items(desc)) return rc;
 
-  // Composition of the general kernels (three passes over the rows).
   const bool grad = g_item != nullptr;
+  if (!grad && d.conditional) {
+    // forward-only evaluation of the conditional posterior: ONE pass (tcgen05 encode, link from on-chip bits)
+    const cudaError_t e5 = vibo::tc5_eval(d, response, mask, table, item_feat, eps_ability, seed, seed_dev,
+                                          out_scalars, ability_mu, ability_logvar, ability, workspace,
+                                          workspace_bytes, st);
+    if (e5 == cudaSuccess) return VIBO_OK;
+    if (e5 != cudaErrorNotSupported) return cuda_fail(e5, "tc5_eval");
+    (void)cudaGetLastError();
+  }
+
+  // Composition of the general kernels (three passes over the rows).
   const size_t PD = (size_t)d.num_person * d.ability_dim;
   const size_t F = (size_t)vibo::item_width_host(d.irt_model, d.ability_dim);
   const size_t G = (size_t)vibo::sm_count() * 8;

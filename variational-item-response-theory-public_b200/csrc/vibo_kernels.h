@@ -104,6 +104,13 @@ cudaError_t tc5_encode_bwd(const vibo_desc& d, const float* resp, const uint8_t*
                            const float* S, const float* g_mu, const float* g_lv, float* part, int* grid_out,
                            cudaStream_t st);
 
+// vibo_tc5_eval.cu: single-pass forward ELBO of the conditional posterior (tcgen05 encode + on-chip link)
+size_t tc5_eval_workspace_bytes();
+cudaError_t tc5_eval(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table,
+                     const float* item_feat, const float* eps, uint64_t seed, const uint64_t* seed_dev,
+                     double* out_scalars, float* amu, float* alv, float* ability, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+
 // vibo_percell.cu: per-cell MLP of the nonlinear generative models on tcgen05 / TMEM (hidden width 64)
 cudaError_t launch_percell_mlp(int64_t P, int I, int u_rows, int v_rows, const float* U, const float* V,
                                const float* Z, const float* w0, const float* W2, const float* c2, const float* w4,
