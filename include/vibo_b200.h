@@ -358,6 +358,9 @@ int vibo_flow_person_backward(const vibo_desc* desc, int n_flows, const float* a
  *   connect   all_handles = the world_size handles in rank order (exchange them with any host
  *             collective, e.g. torch.distributed.all_gather_object); barrier afterwards;
  *   allreduce every rank must issue the same sequence of calls (same n); enqueued on `stream`;
+ *   allreduce_adam  the same exchange followed, in the same kernel, by vibo_adam_step on the summed
+ *             gradients: data[skip + k] is the gradient of param[k], k < n - skip (the training step
+ *             keeps [loss | gradients] in one vector, skip = 1); `step` as for vibo_adam_step;
  *   status    VIBO_OK, or VIBO_ERR_CUDA if a peer failed to arrive within 20 s (synchronises).
  */
 #define VIBO_COMM_HANDLE_BYTES 64
@@ -365,6 +368,9 @@ typedef struct vibo_comm vibo_comm;
 int vibo_comm_create(int rank, int world_size, size_t max_floats, vibo_comm** out, void* handle_out);
 int vibo_comm_connect(vibo_comm* comm, const void* all_handles);
 int vibo_comm_allreduce(vibo_comm* comm, float* data, size_t n, void* stream);
+int vibo_comm_allreduce_adam(vibo_comm* comm, float* data, size_t n, size_t skip, float* param,
+                             float* exp_avg, float* exp_avg_sq, const int64_t* step, float lr,
+                             float beta1, float beta2, float eps, void* stream);
 int vibo_comm_status(vibo_comm* comm);
 int vibo_comm_destroy(vibo_comm* comm);
 const char* vibo_comm_last_error(void);

@@ -73,6 +73,8 @@ SIGNATURES = {
     "vibo_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), _p]),
     "vibo_comm_connect": (C.c_int, [_p, _p]),
     "vibo_comm_allreduce": (C.c_int, [_p, _p, C.c_size_t, _p]),
+    "vibo_comm_allreduce_adam": (C.c_int, [_p, _p, C.c_size_t, C.c_size_t, _p, _p, _p, _p, C.c_float, C.c_float,
+                                           C.c_float, C.c_float, _p]),
     "vibo_comm_status": (C.c_int, [_p]),
     "vibo_comm_destroy": (C.c_int, [_p]),
     "vibo_comm_last_error": (C.c_char_p, []),

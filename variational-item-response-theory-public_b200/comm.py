@@ -51,6 +51,19 @@ class PeerAllReduce:
         self._check(rc, "vibo_comm_allreduce")
         return flat
 
+    def all_reduce_adam_(self, flat, skip, param, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8):
+        """all_reduce_ followed, in the same kernel, by the Adam step on ``flat[skip:]`` (the summed
+        gradients of ``param``); ``step`` is the device-side int64 update count."""
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
+        assert param.numel() == flat.numel() - skip
+        ptr = lambda x: C.c_void_p(x.data_ptr())
+        rc = self.lib.vibo_comm_allreduce_adam(self.handle, ptr(flat), flat.numel(), int(skip), ptr(param),
+                                               ptr(exp_avg), ptr(exp_avg_sq), ptr(step), C.c_float(lr),
+                                               C.c_float(betas[0]), C.c_float(betas[1]), C.c_float(eps),
+                                               C.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream))
+        self._check(rc, "vibo_comm_allreduce_adam")
+        return flat
+
     def status(self):
         self._check(self.lib.vibo_comm_status(self.handle), "vibo_comm_status")
 

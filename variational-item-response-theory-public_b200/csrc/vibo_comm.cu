@@ -20,17 +20,27 @@
 #include <cstring>
 #include <new>
 
+#include "vibo_common.cuh"
 #include "vibo_kernels.h"
 
 namespace vibo {
 
 constexpr int kCommMaxWorld = 16;
-constexpr int kCommMaxBlocks = 16;
-constexpr int kCommThreads = 512;
+constexpr int kCommMaxBlocks = 32;
+constexpr int kCommThreads = 256;
 constexpr size_t kCommFlagBytes = (size_t)kCommMaxBlocks * kCommMaxWorld * sizeof(uint32_t);  // arrival pad
 constexpr size_t kCommEpochOff = kCommFlagBytes;                                              // local epochs
 constexpr size_t kCommErrorOff = kCommEpochOff + 256;                                         // timeout flag
 constexpr size_t kCommSendOff = 4096;
+
+// Optional Adam step on the reduced gradients (vibo_comm_allreduce_adam): element i >= skip of the
+// vector is the gradient of parameter i - skip.
+struct CommAdam {
+  float *param, *m, *v;
+  const int64_t* step;
+  float lr, b1, b2, eps;
+  size_t skip;
+};
 
 struct CommDev {
   char* base[kCommMaxWorld];  // every rank's region (base[rank] is local)
@@ -52,21 +62,40 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   return v;
 }
 
+__device__ __forceinline__ float4 ld_relaxed_sys4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// Every block owns one slice of the vector and runs the whole protocol for it (its own row of
+// the flag pad), so the latency is one flag round trip plus ONE batch of W independent peer loads
+// per thread: the grid is sized so that a thread reduces at most one float4.  All blocks of a call
+// share one epoch (the call count): it selects the send buffer, and every slot of the epoch table
+// is advanced on every call, so calls of different lengths can be mixed freely.
+template <bool ADAM>
 __global__ void __launch_bounds__(kCommThreads) comm_allreduce_kernel(const __grid_constant__ CommDev c,
-                                                                      float* __restrict__ data, size_t n) {
+                                                                      float* __restrict__ data, size_t n,
+                                                                      size_t per, const CommAdam a) {
   __shared__ uint32_t s_epoch;
+  __shared__ float s_bc[2];
+  if (ADAM && threadIdx.x == 32) adam_bias_corrections(a.step, a.b1, a.b2, &s_bc[0], &s_bc[1]);
   const int b = blockIdx.x, t = threadIdx.x;
   char* mine = c.base[c.rank];
-  uint32_t* my_epoch = reinterpret_cast<uint32_t*>(mine + kCommEpochOff) + b;
-  if (t == 0) s_epoch = *my_epoch + 1u;
+  uint32_t* epochs = reinterpret_cast<uint32_t*>(mine + kCommEpochOff);
+  if (t == 0) s_epoch = epochs[b] + 1u;
   __syncthreads();
   const uint32_t e = s_epoch;
   const size_t par_off = kCommSendOff + (size_t)(e & 1u) * c.cap_floats * sizeof(float);
-  const size_t per = (n + gridDim.x - 1) / gridDim.x;
-  const size_t lo = (size_t)b * per, hi = lo + per < n ? lo + per : n;
+  const size_t lo = (size_t)b * per, hi = lo + per < n ? lo + per : n;   // per is a multiple of 4
+  const bool vec = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+  const size_t hi4 = vec ? lo + ((hi - lo) & ~(size_t)3) : lo;
   // 1. my slice -> my send buffer
   float* send = reinterpret_cast<float*>(mine + par_off);
-  for (size_t i = lo + t; i < hi; i += kCommThreads) send[i] = data[i];
+  for (size_t i = lo + 4 * (size_t)t; i < hi4; i += 4 * kCommThreads)
+    *reinterpret_cast<float4*>(send + i) = *reinterpret_cast<const float4*>(data + i);
+  for (size_t i = hi4 + t; i < hi; i += kCommThreads) send[i] = data[i];
   __syncthreads();
   // 2. arrive at every peer, wait for every peer
   if (t < c.world) {
@@ -78,7 +107,7 @@ __global__ void __launch_bounds__(kCommThreads) comm_allreduce_kernel(const __gr
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while ((int32_t)(ld_acquire_sys(my_pad) - e) < 0) {
-      __nanosleep(32);
+      __nanosleep(20);
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 20000000000ull) {
         *reinterpret_cast<uint32_t*>(mine + kCommErrorOff) = 1u;
@@ -87,14 +116,43 @@ __global__ void __launch_bounds__(kCommThreads) comm_allreduce_kernel(const __gr
     }
   }
   __syncthreads();
-  // 3. sum the peers' slices in rank order (identical result on every rank)
-  for (size_t i = lo + t; i < hi; i += kCommThreads) {
+  // 3. sum the peers' slices in rank order (identical result on every rank); the W loads of a
+  //    thread are independent, so they are all in flight together
+  for (size_t i = lo + 4 * (size_t)t; i < hi4; i += 4 * kCommThreads) {
+    float4 v[kCommMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kCommMaxWorld; ++r)
+      if (r < c.world) v[r] = ld_relaxed_sys4(reinterpret_cast<const float*>(c.base[r] + par_off) + i);
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < kCommMaxWorld; ++r)
+      if (r < c.world) {
+        acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w;
+      }
+    *reinterpret_cast<float4*>(data + i) = acc;
+    if (ADAM) {
+      const float g[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (i + q >= a.skip) {
+          const size_t k = i + q - a.skip;
+          adam_update(g[q], a.param + k, a.m + k, a.v + k, a.lr / s_bc[0], s_bc[1], a.b1, a.b2, a.eps);
+        }
+    }
+  }
+  for (size_t i = hi4 + t; i < hi; i += kCommThreads) {
     float acc = 0.0f;
     for (int r = 0; r < c.world; ++r)
       acc += ld_relaxed_sys(reinterpret_cast<const float*>(c.base[r] + par_off) + i);
     data[i] = acc;
+    if (ADAM && i >= a.skip) {
+      const size_t k = i - a.skip;
+      adam_update(acc, a.param + k, a.m + k, a.v + k, a.lr / s_bc[0], s_bc[1], a.b1, a.b2, a.eps);
+    }
   }
-  if (t == 0) *my_epoch = e;
+  // advance the epoch: this block's slot, and (block 0) the slots of the blocks this call did not use
+  if (t == 0) epochs[b] = e;
+  if (b == 0 && t >= (int)gridDim.x && t < kCommMaxBlocks) epochs[t] = e;
 }
 
 }  // namespace vibo
@@ -164,18 +222,39 @@ int vibo_comm_connect(vibo_comm* c, const void* all_handles) {
   return VIBO_OK;
 }
 
-int vibo_comm_allreduce(vibo_comm* c, float* data, size_t n, void* stream) {
+namespace {
+int comm_launch(vibo_comm* c, float* data, size_t n, const vibo::CommAdam* adam, void* stream, const char* who) {
   if (c == nullptr || data == nullptr) return comm_fail(VIBO_ERR_BAD_ARGUMENT, "vibo_comm_allreduce: NULL");
   if (!c->connected && c->dev.world > 1) return comm_fail(VIBO_ERR_BAD_ARGUMENT, "vibo_comm_allreduce: not connected");
   if (n > c->dev.cap_floats) return comm_fail(VIBO_ERR_WORKSPACE, "vibo_comm_allreduce: n exceeds the capacity given at create");
   if (n == 0) return VIBO_OK;
-  int blocks = (int)((n + 4095) / 4096);
+  // one float4 per thread while the blocks last, equal 4-aligned slices beyond that
+  int blocks = (int)((n + 4 * vibo::kCommThreads - 1) / (4 * vibo::kCommThreads));
   if (blocks > vibo::kCommMaxBlocks) blocks = vibo::kCommMaxBlocks;
-  vibo::comm_allreduce_kernel<<<blocks, vibo::kCommThreads, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, data, n);
+  const size_t per = ((n + blocks - 1) / blocks + 3) / 4 * 4;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (adam != nullptr)
+    vibo::comm_allreduce_kernel<true><<<blocks, vibo::kCommThreads, 0, st>>>(c->dev, data, n, per, *adam);
+  else
+    vibo::comm_allreduce_kernel<false><<<blocks, vibo::kCommThreads, 0, st>>>(c->dev, data, n, per, vibo::CommAdam{});
   vibo::note_launch();
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return comm_fail(VIBO_ERR_CUDA, "comm_allreduce_kernel", e);
+  if (e != cudaSuccess) return comm_fail(VIBO_ERR_CUDA, who, e);
   return VIBO_OK;
+}
+}  // namespace
+
+int vibo_comm_allreduce(vibo_comm* c, float* data, size_t n, void* stream) {
+  return comm_launch(c, data, n, nullptr, stream, "comm_allreduce_kernel");
+}
+
+int vibo_comm_allreduce_adam(vibo_comm* c, float* data, size_t n, size_t skip, float* param, float* exp_avg,
+                             float* exp_avg_sq, const int64_t* step, float lr, float beta1, float beta2,
+                             float eps, void* stream) {
+  if (param == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || step == nullptr || skip > n)
+    return comm_fail(VIBO_ERR_BAD_ARGUMENT, "vibo_comm_allreduce_adam: bad argument");
+  const vibo::CommAdam a{param, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, skip};
+  return comm_launch(c, data, n, &a, stream, "comm_allreduce_kernel<adam>");
 }
 
 int vibo_comm_status(vibo_comm* c) {

@@ -119,6 +119,25 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k
   }
 }
 
+// torch.optim.Adam (amsgrad off, no weight decay), one element; bc1 = 1 - b1^t, bc2_sqrt = sqrt(1 - b2^t).
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / bc1 * m / (sqrt(v) / bc2_sqrt + eps)
+__device__ __forceinline__ void adam_update(float g, float* __restrict__ param, float* __restrict__ m,
+                                            float* __restrict__ v, float step_size, float bc2_sqrt, float b1,
+                                            float b2, float eps) {
+  const float mk = fmaf(b1, *m, (1.0f - b1) * g);
+  const float vk = fmaf(b2, *v, (1.0f - b2) * g * g);
+  *m = mk;
+  *v = vk;
+  const float denom = sqrtf(vk) / bc2_sqrt + eps;
+  *param -= step_size * (mk / denom);
+}
+__device__ __forceinline__ void adam_bias_corrections(const int64_t* step, float b1, float b2, float* bc1,
+                                                      float* bc2_sqrt) {
+  const double t = (double)*step;
+  *bc1 = (float)(1.0 - pow((double)b1, t));
+  *bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+}
+
 // Four standard normals for (seed, person, block): Box-Muller on the four Philox words with the
 // MUFU approximations (lg2 / sin / cos; absolute error ~1e-6, irrelevant for noise).  The angle is
 // taken in [-pi, pi] where sin.approx / cos.approx are most accurate:

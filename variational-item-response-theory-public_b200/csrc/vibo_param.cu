@@ -257,23 +257,12 @@ __global__ void __launch_bounds__(256)
 adam_kernel(int n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
             float* __restrict__ v, const int64_t* __restrict__ step, float lr, float b1, float b2, float eps) {
   __shared__ float s_bc[2];
-  if (threadIdx.x == 0) {
-    const double t = (double)*step;
-    s_bc[0] = (float)(1.0 - pow((double)b1, t));
-    s_bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
-  }
+  if (threadIdx.x == 0) adam_bias_corrections(step, b1, b2, &s_bc[0], &s_bc[1]);
   __syncthreads();
-  const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
-  const float step_size = lr / bc1;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const float g = grad[k];
-    const float mk = fmaf(b1, m[k], (1.0f - b1) * g);
-    const float vk = fmaf(b2, v[k], (1.0f - b2) * g * g);
-    m[k] = mk;
-    v[k] = vk;
-    const float denom = sqrtf(vk) / bc2_sqrt + eps;
-    param[k] -= step_size * (mk / denom);
-  }
+  const float bc2_sqrt = s_bc[1];
+  const float step_size = lr / s_bc[0];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    adam_update(grad[k], param + k, m + k, v + k, step_size, bc2_sqrt, b1, b2, eps);
 }
 
 // Dynamic shared memory of the staged weights; 0 (not staged) when they do not fit.

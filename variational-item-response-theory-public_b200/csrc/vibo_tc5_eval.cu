@@ -41,6 +41,7 @@ constexpr int kE5ThLd = 8;   // floats per person in the theta tile
 struct E5Params {
   int64_t P;
   int I, n_kb, missing_policy, form;
+  int debug;   // VIBO_E5_DEBUG (attribution runs only): 1 skip the link arithmetic, 2 skip the bit packing, 4 skip the mask scan
   int64_t person_offset;
   const float* resp;
   const uint8_t* mask;
@@ -119,6 +120,41 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// Log-likelihood of TWO cells (the warp's two item blocks for one person) in packed f32x2 arithmetic,
+// forward only; same clamp semantics as link_cell / cell_logistic_fast (vibo_stream_kernel.cuh): the
+// probability is clamped to [eps32, 1 - eps32] (utils.py:46-49 -> torch Bernoulli).  x0 / x1: the cell is 1.
+// Returns (ll0, ll1) in log2 units for the 3PL (caller scales by ln 2) / natural units for 1PL / 2PL.
+template <int MODEL>
+__device__ __forceinline__ f2_t eval_pair(f2_t z2, bool x0, bool x1, f2_t g2, f2_t omg2) {
+  float z0, z1;
+  unpack2(z2, z0, z1);
+  if (MODEL == 3) {
+    const f2_t zc2 = pack2(fmaxf(z0, -80.0f), fmaxf(z1, -80.0f));
+    float t0, t1;
+    unpack2(mul2(zc2, pack2(-kLog2e, -kLog2e)), t0, t1);
+    const f2_t e2 = pack2(ex2_approx(t0), ex2_approx(t1));
+    float w0, w1;
+    unpack2(add2(e2, pack2(1.0f, 1.0f)), w0, w1);
+    const f2_t r2 = pack2(rcp_approx(w0), rcp_approx(w1));
+    const f2_t pp2 = fma2(omg2, r2, g2);            // p = g + (1 - g) sigmoid(z)
+    const f2_t q2 = mul2(omg2, mul2(e2, r2));       // 1 - p = (1 - g) sigmoid(-z), full relative precision
+    float p0, p1, q0, q1;
+    unpack2(pp2, p0, p1);
+    unpack2(q2, q0, q1);
+    const float u0 = fminf(fmaxf(x0 ? p0 : q0, kEps32), 1.0f - kEps32);
+    const float u1 = fminf(fmaxf(x1 ? p1 : q1, kEps32), 1.0f - kEps32);
+    return pack2(lg2_approx(u0), lg2_approx(u1));
+  } else {
+    // ll = (x - 1) zc - log(1 + exp(-zc)),  zc = clamp(z, +-15.942385)
+    const f2_t zc2 = pack2(fminf(fmaxf(z0, -kLogitClamp), kLogitClamp), fminf(fmaxf(z1, -kLogitClamp), kLogitClamp));
+    float t0, t1;
+    unpack2(mul2(zc2, pack2(-kLog2e, -kLog2e)), t0, t1);
+    const f2_t l2 = pack2(lg2_approx(1.0f + ex2_approx(t0)), lg2_approx(1.0f + ex2_approx(t1)));
+    const f2_t xm2 = pack2(x0 ? 0.0f : -1.0f, x1 ? 0.0f : -1.0f);
+    return fma2(l2, pack2(-kLn2f, -kLn2f), mul2(xm2, zc2));
+  }
+}
 
 template <int MODEL, int D>
 __global__ void __launch_bounds__(kE5Threads, 1)
@@ -268,7 +304,7 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const int64_t len = (int64_t)rows * I, n16 = len >> 4;
         const uint4* m16 = reinterpret_cast<const uint4*>(mb);
         constexpr int B = 16;
-        for (int64_t k0 = e; k0 < n16; k0 += 128 * B) {
+        for (int64_t k0 = e; k0 < ((p.debug & 4) ? 0 : n16); k0 += 128 * B) {
           uint4 w[B];
 #pragma unroll
           for (int u = 0; u < B; ++u) {
@@ -405,16 +441,21 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       for (int kb = 0; kb < p.n_kb; ++kb) {
         bar_wait(full(s), ph);
         const uint32_t st = st_base + (uint32_t)s * kE5StageBytes + (uint32_t)pw * 32u * 128u;
+        // pull the warp's 32 x 32 cells into registers and hand the stage back at once: the ballots
+        // below then run off the ring's critical path
+        uint32_t xs[32];
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) xs[rr] = lds32(st + (uint32_t)(rr >> 3) * 1024u + off8[rr & 7]);
+        __syncwarp();
+        if (lane == 0) bar_arrive(empty(s));   // this warp's reads of the stage are complete
         uint32_t mine = 0;
+        if (!(p.debug & 2))
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr) {
-          const float x = __uint_as_float(lds32(st + (uint32_t)(rr >> 3) * 1024u + off8[rr & 7]));
-          const uint32_t w = __ballot_sync(0xffffffffu, x > 0.5f);
+          const uint32_t w = __ballot_sync(0xffffffffu, __uint_as_float(xs[rr]) > 0.5f);
           mine = lane == rr ? w : mine;   // lane rr keeps the word of person 32 pw + rr
         }
         bits[kb * kE5Rows + pw * 32 + lane] = mine;
-        __syncwarp();
-        if (lane == 0) bar_arrive(empty(s));   // this warp's reads of the stage are complete
         if (++s == kE5Stages) {
           s = 0;
           ph ^= 1u;
@@ -448,6 +489,15 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       omg[q] = 1.0f - gj[q];
       wv[q] = valid ? 1.0f : 0.0f;
     }
+    // the two item blocks as f32x2 pairs; the validity weight (and ln 2 for the 3PL) folded into one scale
+    f2_t na2[MODEL == 1 ? 1 : D];
+#pragma unroll
+    for (int d = 0; d < (MODEL == 1 ? 1 : D); ++d) na2[d] = pack2(-a[0][d], -a[1][d]);
+    const f2_t b2 = pack2(bj[0], bj[1]), g2 = pack2(gj[0], gj[1]), omg2 = pack2(omg[0], omg[1]);
+    const float sc = MODEL == 3 ? kLn2f : 1.0f;
+    const f2_t scale2 = pack2(wv[0] * sc, wv[1] * sc);
+    const uint32_t lane_bit = 1u << lane;
+    const int kb0 = lw & 31, kb1 = (lw + 16) & 31;
     int b = 0;
     uint32_t tph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -455,34 +505,27 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const float* th_tile = s_theta + b * kE5Rows * kE5ThLd;
       const uint8_t* s_flag = s_flags + b * kE5Rows;
       bar_wait(theta_full(b), tph);
-      float ll_lane = 0.0f;
+      f2_t ll2 = pack2(0.0f, 0.0f);
 #pragma unroll 2
-      for (int pr = 0; pr < kE5Rows; ++pr) {
+      for (int pr = 0; pr < ((p.debug & 1) ? 0 : kE5Rows); ++pr) {
         if (s_flag[pr] != 0) continue;   // missing cells (handled by the epilogue) or past the end
-        float th[D], tsum = 0.0f;
         const float4 t4 = *reinterpret_cast<const float4*>(th_tile + pr * kE5ThLd);
         const float4 t5 = *reinterpret_cast<const float4*>(th_tile + pr * kE5ThLd + 4);
         const float tv[8] = {t4.x, t4.y, t4.z, t4.w, t5.x, t5.y, t5.z, t5.w};
+        f2_t z2 = b2;
+        if (MODEL == 1) {
+          z2 = add2(z2, pack2(tv[7], tv[7]));
+        } else {
 #pragma unroll
-        for (int d = 0; d < D; ++d) th[d] = tv[d];
-        if (MODEL == 1) tsum = tv[7];
-#pragma unroll
-        for (int q = 0; q < NB; ++q) {
-          const uint32_t w = bits[((lw + 16 * q) & 31) * kE5Rows + pr];
-          const float x = (float)((w >> lane) & 1u);
-          float z = bj[q];
-          if (MODEL == 1) {
-            z += tsum;
-          } else {
-#pragma unroll
-            for (int d = 0; d < D; ++d) z = fmaf(-th[d], a[q][d], z);
-          }
-          float l1, dz, t0;
-          link_cell<MODEL>(z, x, gj[q], omg[q], wv[q], l1, dz, t0);
-          ll_lane = fmaf(wv[q], l1, ll_lane);
+          for (int d = 0; d < D; ++d) z2 = fma2(pack2(tv[d], tv[d]), na2[d], z2);
         }
+        const bool x0 = (bits[kb0 * kE5Rows + pr] & lane_bit) != 0;
+        const bool x1 = (bits[kb1 * kE5Rows + pr] & lane_bit) != 0;
+        ll2 = fma2(eval_pair<MODEL>(z2, x0, x1, g2, omg2), scale2, ll2);
       }
-      acc_ll += (double)ll_lane;
+      float l0, l1;
+      unpack2(ll2, l0, l1);
+      acc_ll += (double)(l0 + l1);
       __syncwarp();
       if (lane == 0) bar_arrive(tile_done(b));
       b ^= 1;
@@ -581,7 +624,8 @@ cudaError_t tc5_eval(const vibo_desc& d, const float* resp, const uint8_t* mask,
   if (enc == nullptr) return cudaErrorNotSupported;
   E5Params p;
   p.P = d.num_person; p.I = I; p.n_kb = (I + kE5KB - 1) / kE5KB; p.missing_policy = d.missing_policy;
-  p.form = d.elbo_form; p.person_offset = d.person_offset; p.resp = resp; p.mask = mask; p.table = table;
+  p.form = d.elbo_form; p.person_offset = d.person_offset;
+  { const char* dbg = getenv("VIBO_E5_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; } p.resp = resp; p.mask = mask; p.table = table;
   p.item_feat = item_feat; p.eps = eps; p.seed = seed; p.seed_dev = seed_dev;
   const bool person_out = amu != nullptr && alv != nullptr && ability != nullptr;
   p.out_mu = person_out ? amu : nullptr; p.out_lv = person_out ? alv : nullptr;

@@ -38,7 +38,7 @@ class FusedStep:
     libvibo_b200.so and nothing else (no autograd, no torch kernels):
 
         vibo_param_forward[_draw] -> vibo_fused_elbo[_graph] (+ finalize) -> vibo_step_tail
-        [-> all-reduce] -> vibo_adam_step
+        [-> all-reduce] -> vibo_adam_step   (peer-memory exchange: all-reduce + Adam are one kernel)
 
     Parameters, gradients and Adam moments live in flat buffers; the module's parameters are
     re-homed as views of ``theta`` (state_dict / load_state_dict keep working), ``p.grad`` are
@@ -143,6 +143,10 @@ class FusedStep:
                                        ptr(self.adam_step) if train else None, ptr(mu), ptr(lv), ptr(e_i),
                                        ptr(w2), ptr(w4), ptr(self.hidden), ptr(self.g_table), ptr(self.g_item),
                                        *grads, st), "vibo_step_tail")
+        if train and t.world_size > 1 and t.peer is not None:
+            # the exchange and the Adam step as one kernel over NVLink peer memory
+            t.peer.all_reduce_adam_(flat, 1, self.theta, self.exp_avg, self.exp_avg_sq, self.adam_step, self.lr)
+            return
         t._reduce(flat if train else flat[0:1])
         if train:
             self._check(lib.vibo_adam_step(self.n, ptr(self.theta), C.c_void_p(flat.data_ptr() + 4),
