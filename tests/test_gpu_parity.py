@@ -93,18 +93,30 @@ GRID = [
     (129, 36, 1, 1, True, 0.0, 0, 0),
     (257, 100, 2, 3, True, 0.3, 1, 1),
     (64, 1500, 2, 3, False, 0.2, 0, 0),
+    # item-owner training kernel (unconditional 1PL / 2PL, I >= 384): both models, D = 2, prior policy,
+    # sample form, ragged last chunk, second item group partly / fully unused, widest rows
+    (600, 400, 1, 1, False, 0.05, 0, 0),
+    (500, 384, 2, 2, False, 0.1, 1, 1),
+    (1030, 1024, 2, 2, False, 0.0, 0, 0),
+    (2203, 996, 1, 2, False, 0.0, 0, 1),
+    (3001, 512, 1, 1, False, 0.0, 0, 0),
 ]
 
 
 # which implementation serves the call:
-#   fused    - single-pass kernel where it applies, else the composition below
+#   fused    - single-pass kernel where it applies (item-owner kernel for training with I >= 384, two-phase
+#              kernel otherwise), else the composition below
+#   fused2   - the same with the item-owner kernel disabled
 #   composed - three passes: tensor-core encode (tcgen05 / TMEM / 2-D TMA where D <= 5 and I % 4 == 0,
 #              else mma.sync) and mma.sync encode-backward for a conditional posterior, slab-stream
 #              kernels otherwise
 #   mma      - the same with the tcgen05 encode disabled (VIBO_DISABLE_TC5=1)
 #   slab     - three passes, slab-stream kernels only (VIBO_DISABLE_MMA=1)
 #   legacy   - three passes, the original row-slab kernels (unaligned-pointer fallback)
-PATHS = {"fused": {}, "composed": {"VIBO_DISABLE_FUSED": "1"},
+PATHS = {"fused": {},
+         # training on the two-phase kernel where the item-owner kernel would serve
+         "fused2": {"VIBO_DISABLE_FUSED3": "1"},
+         "composed": {"VIBO_DISABLE_FUSED": "1"},
          # conditional encode on mma.sync instead of the tcgen05 / TMA kernel
          "mma": {"VIBO_DISABLE_FUSED": "1", "VIBO_DISABLE_TC5": "1"},
          "slab": {"VIBO_DISABLE_FUSED": "1", "VIBO_DISABLE_MMA": "1"},
@@ -119,6 +131,8 @@ def test_fused_elbo_vs_oracle(vb, monkeypatch, P, I, D, irt, cond, missing, poli
         monkeypatch.setenv(k, v)
     if path == "legacy" and I > 1024 and D > 4:
         pytest.skip("legacy kernels: I <= 1024 for D > 4")
+    if path == "fused2" and (cond or irt == 3 or I < 384 or I > 1024 or I % 4):
+        pytest.skip("same kernel as the 'fused' path for this shape")
     resp, mask, table, item, eps = _synth(P, I, D, irt, cond, missing, seed=P * 7 + I)
     beta = 0.7
     got = _run_fused(vb, resp, mask, table, item, eps, irt_model=irt, conditional=cond,
@@ -235,6 +249,23 @@ def test_param_chain_kernels_match_autograd(vb, irt, D, use_kl):
     assert abs(out[True][0] - out[False][0]) <= 1e-6 * abs(out[False][0])
     for k, gref in out[False][1].items():
         assert rel_l2(out[True][1][k].cpu().numpy(), gref.cpu().numpy()) < 1e-5, k
+
+
+@pytest.mark.parametrize("irt,D,missing", [(2, 1, 0.0), (2, 2, 0.15), (1, 1, 0.0), (1, 1, 0.2)])
+def test_owner_kernel_saturating_rows(vb, irt, D, missing):
+    """Wide rows whose logits pass the eps32 clamp (row-level exact path, all observed and with missing
+    cells) next to rows that stay on the fast path, through the item-owner training kernel."""
+    P, I = 700, 1000
+    resp, mask, table, item, eps = _synth(P, I, D, irt, False, missing, seed=99 + irt + D)
+    item[:, -1] *= 4.0                      # difficulties up to ~ +-10
+    eps[::3] *= 6.0                         # every third person far out: |z| > 15.94 for many cells
+    table[:, :, D:] += 3.0                  # wide posteriors so the draw matters
+    mask[5] = 1
+    resp[5] = (resp[5] > 0).astype(np.float32)
+    got = _run_fused(vb, resp, mask, table, item, eps, irt_model=irt, conditional=False, beta=0.5)
+    ref = KS.fused_elbo(resp.astype(np.float64), mask, table.astype(np.float64), item.astype(np.float64),
+                        eps.astype(np.float64), irt_model=irt, beta=0.5)
+    _check_fused(got, ref)
 
 
 def test_saturated_cells(vb):

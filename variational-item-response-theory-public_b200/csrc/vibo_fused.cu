@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "vibo_fused2_kernel.cuh"
+#include "vibo_fused3_kernel.cuh"
 
 namespace vibo {
 
@@ -230,6 +231,12 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
   { const char* dbg = getenv("VIBO_FUSED_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; } p.resp = resp; p.mask = mask; p.eps = eps;
   p.eps_draw = eps_draw; p.seed = seed; p.seed_dev = seed_dev; p.person_offset = d.person_offset;
   p.item_feat = item_feat; p.table = table;
+  {
+    const int n_teams = pl.two_phase ? kF2Teams : kFusedTeams;
+    const FusedSmem L = fused_smem_layout(d.num_item, D, d.irt_model, pl.R, pl.nstage, n_teams,
+                                          pl.two_phase ? f2_scratch_bytes(pl.R, pl.nstage, D) : 0);
+    p.mask_off = (int)L.mask_off; p.eps_off = (int)L.eps_off; p.stage_bytes = (int)L.stage_bytes;
+  }
   const bool person_out = amu != nullptr && alv != nullptr && ability != nullptr;
   p.out_mu = person_out ? amu : nullptr; p.out_lv = person_out ? alv : nullptr;
   p.out_theta = person_out ? ability : nullptr;
@@ -246,7 +253,15 @@ cudaError_t launch_fused(const vibo_desc& d, const float* resp, const uint8_t* m
     cudaEventRecord(ev.a, st);
   }
   cudaError_t e = cudaErrorNotSupported;
-  if (pl.two_phase) {
+  // training with wide rows: the item-owner kernel (same plan, same partials); VIBO_DISABLE_FUSED3=1
+  // keeps the two-phase kernel (differential tests)
+  const char* no3 = getenv("VIBO_DISABLE_FUSED3");
+  const bool owner_kernel = pl.two_phase && grad && (d.num_item >> 2) >= kF3MinGroups && !(no3 && no3[0] == '1');
+  if (owner_kernel) {
+    if (d.irt_model == 1 && D == 1) e = launch_fused3_md<1, 1>(p, pl.grid, pl.smem, st);
+    else if (d.irt_model == 2 && D == 1) e = launch_fused3_md<2, 1>(p, pl.grid, pl.smem, st);
+    else if (d.irt_model == 2 && D == 2) e = launch_fused3_md<2, 2>(p, pl.grid, pl.smem, st);
+  } else if (pl.two_phase) {
     if (d.irt_model == 1 && D == 1) e = launch_fused2_md<1, 1>(p, pl.grid, pl.smem, grad, st);
     else if (d.irt_model == 2 && D == 1) e = launch_fused2_md<2, 1>(p, pl.grid, pl.smem, grad, st);
     else if (d.irt_model == 2 && D == 2) e = launch_fused2_md<2, 2>(p, pl.grid, pl.smem, grad, st);

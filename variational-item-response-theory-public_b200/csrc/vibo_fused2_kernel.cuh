@@ -44,7 +44,9 @@ constexpr int kF2MaxRows = 64;            // rows per stage upper bound (team sc
 //                  in phase B, hence one copy per slot)
 constexpr int kF2SumOff = 64, kF2ThetaOff = 576;
 __host__ __device__ inline int f2_scratch_bytes(int R, int NS, int D) {
-  return kF2ThetaOff + kF2Teams * NS * R * D * 8;
+  const int theta = kF2Teams * NS * R * D * 8;
+  const int owner = kF2Teams * 768;   // fused3_kernel (same plan): per-team counts, g_theta partials, table sums
+  return kF2ThetaOff + (theta > owner ? theta : owner);
 }
 
 // ---- packed f32x2 arithmetic (FFMA2 / FADD2 / FMUL2): two floats per issue slot ----

@@ -49,6 +49,7 @@ struct FusedParams {
   int missing_policy;
   float beta;
   int debug;    // 0 normal; 1 stream only (no math); 2 math only (no refills)  [VIBO_FUSED_DEBUG]
+  int mask_off, eps_off, stage_bytes;   // fused_smem_layout of this launch (host-computed copies: one constant load each)
   const float* resp;
   const uint8_t* mask;
   const float* eps;        // (P, D) standard normals the rows are staged from
