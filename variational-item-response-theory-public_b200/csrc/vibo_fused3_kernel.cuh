@@ -97,9 +97,8 @@ __device__ __forceinline__ float f3_reduce4(const float (&v)[4], int lane) {
   return k;   // lane 0: v[0], lane 8: v[1], lane 16: v[2], lane 24: v[3]
 }
 
-// Refill of one stage.  A whole chunk goes as three bulk copies addressed through the host-computed layout
-// offsets; the (only possibly) ragged last chunk takes the shared routine out of line, so that its
-// layout arithmetic stays out of the hot loop.
+// Refill with the grid's ragged last chunk (sizes not 16-byte multiples: copied by hand by one warp), out of
+// line so that its layout arithmetic stays out of the hot loop.
 template <int MODEL, int D>
 __device__ __noinline__ void f3_issue_ragged(const FusedParams& p, int64_t c, int team, int s, int lane) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -107,26 +106,6 @@ __device__ __noinline__ void f3_issue_ragged(const FusedParams& p, int64_t c, in
   unsigned char* st = smem + L.stage_off + ((size_t)team * p.nstage + s) * L.stage_bytes;
   fused_issue_chunk<D>(p, L, c, st, reinterpret_cast<uint64_t*>(smem) + team * p.nstage + s, lane);
 }
-template <int MODEL, int D>
-__device__ __forceinline__ void f3_issue_chunk(const FusedParams& p, int64_t c, uint32_t sb, uint32_t bar, int team,
-                                               int s, int lane) {
-  const int64_t row0 = c * p.R;
-  if (p.P - row0 >= p.R) {   // rows per stage keep every copy a 16-byte multiple (fused_plan)
-    if (lane == 0) {
-      const uint32_t b_resp = (uint32_t)p.R * p.I * 4u, b_mask = (uint32_t)p.R * p.I, b_eps = (uint32_t)p.R * D * 4u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_resp + b_mask + b_eps) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
-                   "l"(p.resp + row0 * p.I), "r"(b_resp), "r"(bar) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb + (uint32_t)p.mask_off),
-                   "l"(p.mask + row0 * p.I), "r"(b_mask), "r"(bar) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb + (uint32_t)p.eps_off),
-                   "l"(p.eps + row0 * D), "r"(b_eps), "r"(bar) : "memory");
-    }
-  } else {
-    f3_issue_ragged<MODEL, D>(p, c, team, s, lane);
-  }
-}
-
 template <int MODEL, int D>
 __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_constant__ FusedParams p) {
   static_assert(MODEL == 1 || MODEL == 2, "item-owner kernel covers 1PL / 2PL");
@@ -142,8 +121,6 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
   const int I = p.I, R = p.R, NS = p.nstage;
   const FusedSmem L = fused_smem_layout(I, D, MODEL, R, NS, NQ, f2_scratch_bytes(R, NS, D));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);   // [NQ * NS] (<= 16)
-  int* done_cnt = reinterpret_cast<int*>(smem + 128);
-  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + 256);
   float* s_max = reinterpret_cast<float*>(smem + kFusedHdr);      // amax[0..7], bmax, sum a'[0..1], sum b'
   double* s_wsum = reinterpret_cast<double*>(smem + kFusedHdr + kF2SumOff);   // [warp][3] setup partials
   float* s_param = reinterpret_cast<float*>(smem + L.params_off);
@@ -154,8 +131,6 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
   const int64_t n_chunks = (p.P + R - 1) / R;
   const int64_t chunk0 = (int64_t)blockIdx.x * NQ + team, chunk_step = (int64_t)gridDim.x * NQ;
   uint64_t* t_full = full_bar + team * NS;
-  int* t_done = done_cnt + team * NS;
-  uint64_t* t_empty = empty_bar + team * NS;
   unsigned char* t_stage = smem + L.stage_off + (size_t)team * NS * L.stage_bytes;
   // team scratch (the region fused2 keeps its theta rows in)
   int* t_cnt = reinterpret_cast<int*>(smem + kFusedHdr + kF2ThetaOff + team * kF3TeamScratch);
@@ -164,8 +139,6 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < NQ * NS; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], TW);
-      done_cnt[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -300,6 +273,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
   float amu[D], invS[D], sd[D], th[D], epsv[D];
   float n0f = 0.0f, n1f = 0.0f;
   bool pending = false;   // owner thread: a row of the previous block awaits its backward
+  // a stage is released by the team barrier that follows its last block (every warp has left it by then):
+  // the refill is issued right after that barrier, one bulk copy per warp
+  bool refill = false;
+  int refill_s = 0, refill_it = 0;
   uint32_t bp = 0;        // block parity: which copy of the counts / partials this block writes
   auto row_backward = [&](uint32_t gth_prev) {
 #pragma unroll
@@ -412,6 +389,30 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(cntb + (uint32_t)wt * 16u), "r"(c_n1a),
                      "r"(c_n1b), "r"(c_noa), "r"(c_nob) : "memory");
       team_barrier(team);
+      if (refill) {   // team-uniform
+        refill = false;
+        const int64_t row0 = (chunk0 + (int64_t)(refill_it + NS) * chunk_step) * R;
+        const uint32_t dst = stage0 + (uint32_t)refill_s * stage_bytes, bar = bar0 + (uint32_t)refill_s * 8u;
+        if (p.P - row0 >= R) {   // a whole chunk: every copy is a 16-byte multiple (fused_plan)
+          const uint32_t b_resp = (uint32_t)R * I * 4u, b_mask = (uint32_t)R * I, b_eps = (uint32_t)R * D * 4u;
+          if (lane == 0) {
+            if (wt == 0) {
+              // the phase cannot complete before this arrival, whatever the order of the three copies
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_resp + b_mask + b_eps) : "memory");
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                           "l"(p.resp + row0 * I), "r"(b_resp), "r"(bar) : "memory");
+            } else if (wt == 1) {
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (uint32_t)p.mask_off),
+                           "l"(p.mask + row0 * I), "r"(b_mask), "r"(bar) : "memory");
+            } else if (wt == 2) {
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (uint32_t)p.eps_off),
+                           "l"(p.eps + row0 * D), "r"(b_eps), "r"(bar) : "memory");
+            }
+          }
+        } else if (wt == 3) {
+          f3_issue_ragged<MODEL, D>(p, row0 / R, team, refill_s, lane);   // the grid's ragged last chunk
+        }
+      }
 
       // ---- backward of the previous block's rows (their 4 partials are complete now) -------------
       if (pending) row_backward(cnt0 + kF3Gth + (bp ^ 1u) * 128u);
@@ -618,23 +619,11 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
         }
       }
 
-      // the stage's last block of rows has been read: the last warp to get here hands the stage back
-      if (rbase + 4 >= rows) {
-        if (p.debug == 3) team_barrier(team);
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-          mbar_arrive(&t_empty[s]);
-          __threadfence_block();
-          last = atomicAdd(&t_done[s], 1) == TW - 1;
-          if (last) atomicExch(&t_done[s], 0);
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last && it + NS < n_it) {
-          const int64_t cn = chunk0 + (int64_t)(it + NS) * chunk_step;
-          mbar_wait(&t_empty[s], phase);
-          f3_issue_chunk<MODEL, D>(p, cn, sb, bar0 + (uint32_t)s * 8, team, s, lane);
-        }
+      // the stage's last block of rows has been read: refill it after the next team barrier
+      if (rbase + 4 >= rows && it + NS < n_it) {
+        refill = true;
+        refill_s = s;
+        refill_it = it;
       }
     }
     if (++s == NS) {
