@@ -106,7 +106,7 @@ __device__ __noinline__ void f3_issue_ragged(const FusedParams& p, int64_t c, in
   unsigned char* st = smem + L.stage_off + ((size_t)team * p.nstage + s) * L.stage_bytes;
   fused_issue_chunk<D>(p, L, c, st, reinterpret_cast<uint64_t*>(smem) + team * p.nstage + s, lane);
 }
-template <int MODEL, int D>
+template <int MODEL, int D, int NGB>   // NGB: 4-item groups per thread (1: I <= 512, 2: I <= 1024)
 __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_constant__ FusedParams p) {
   static_assert(MODEL == 1 || MODEL == 2, "item-owner kernel covers 1PL / 2PL");
   static_assert(D <= 2, "setup sums / accumulators are sized for D <= 2");
@@ -114,7 +114,6 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
   constexpr int DA = MODEL == 1 ? 0 : D;
   constexpr int DP = DA > 0 ? DA : 1;
   constexpr int TW = kF2TeamWarps, NQ = kF2Teams;
-  constexpr int NGB = kF2GroupsPerThread;
   constexpr float kLn2 = 0.6931471805599453f;
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -277,6 +276,15 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
   // the refill is issued right after that barrier, one bulk copy per warp
   bool refill = false;
   int refill_s = 0, refill_it = 0;
+  // warp 0 copies the responses, warp 1 the mask, warp 2 the noise: each keeps the global address of its
+  // next copy and advances it by one round of the grid's teams per refill
+  const uint32_t cp_row = wt == 0 ? (uint32_t)I * 4u : (wt == 1 ? (uint32_t)I : (uint32_t)D * 4u);   // bytes per row
+  const uint32_t cp_bytes = (uint32_t)R * cp_row;
+  const uint32_t cp_off = wt == 0 ? 0u : (wt == 1 ? (uint32_t)p.mask_off : (uint32_t)p.eps_off);
+  const char* cp_src = (wt == 0 ? reinterpret_cast<const char*>(p.resp)
+                                : (wt == 1 ? reinterpret_cast<const char*>(p.mask) : reinterpret_cast<const char*>(p.eps))) +
+                       (chunk0 + (int64_t)NS * chunk_step) * R * (int64_t)cp_row;
+  const bool ragged_last = owns_last && last_rows != R;   // the grid's last chunk is partial and this team's
   uint32_t bp = 0;        // block parity: which copy of the counts / partials this block writes
   auto row_backward = [&](uint32_t gth_prev) {
 #pragma unroll
@@ -391,26 +399,19 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
       team_barrier(team);
       if (refill) {   // team-uniform
         refill = false;
-        const int64_t row0 = (chunk0 + (int64_t)(refill_it + NS) * chunk_step) * R;
         const uint32_t dst = stage0 + (uint32_t)refill_s * stage_bytes, bar = bar0 + (uint32_t)refill_s * 8u;
-        if (p.P - row0 >= R) {   // a whole chunk: every copy is a 16-byte multiple (fused_plan)
-          const uint32_t b_resp = (uint32_t)R * I * 4u, b_mask = (uint32_t)R * I, b_eps = (uint32_t)R * D * 4u;
-          if (lane == 0) {
-            if (wt == 0) {
-              // the phase cannot complete before this arrival, whatever the order of the three copies
-              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_resp + b_mask + b_eps) : "memory");
-              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                           "l"(p.resp + row0 * I), "r"(b_resp), "r"(bar) : "memory");
-            } else if (wt == 1) {
-              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (uint32_t)p.mask_off),
-                           "l"(p.mask + row0 * I), "r"(b_mask), "r"(bar) : "memory");
-            } else if (wt == 2) {
-              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (uint32_t)p.eps_off),
-                           "l"(p.eps + row0 * D), "r"(b_eps), "r"(bar) : "memory");
-            }
+        if (!(ragged_last && refill_it + NS == n_it - 1)) {   // a whole chunk: every copy a 16-byte multiple (fused_plan)
+          if (lane == 0 && wt < 3) {
+            // the phase cannot complete before warp 0's arrival, whatever the order of the three copies
+            if (wt == 0)
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                           "r"((uint32_t)R * ((uint32_t)I * 5u + (uint32_t)D * 4u)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + cp_off),
+                         "l"(cp_src), "r"(cp_bytes), "r"(bar) : "memory");
           }
+          cp_src += (size_t)cp_bytes * (size_t)chunk_step;
         } else if (wt == 3) {
-          f3_issue_ragged<MODEL, D>(p, row0 / R, team, refill_s, lane);   // the grid's ragged last chunk
+          f3_issue_ragged<MODEL, D>(p, chunk0 + (int64_t)(refill_it + NS) * chunk_step, team, refill_s, lane);
         }
       }
 
@@ -711,14 +712,20 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
 template <int MODEL, int D>
 cudaError_t launch_fused3_md(const FusedParams& p, int grid, size_t smem, cudaStream_t st);
 
+template <int MODEL, int D, int NGB>
+static cudaError_t launch_fused3_cfg(const FusedParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto k = fused3_kernel<MODEL, D, NGB>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<grid, kF2Threads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
 #define VIBO_FUSED3_INSTANTIATE(MODEL, D)                                                              \
   template <>                                                                                          \
   cudaError_t launch_fused3_md<MODEL, D>(const FusedParams& p, int grid, size_t smem, cudaStream_t st) { \
-    auto k = fused3_kernel<MODEL, D>;                                                                  \
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return e;                                                                    \
-    k<<<grid, kF2Threads, smem, st>>>(p);                                                              \
-    return cudaGetLastError();                                                                         \
+    if ((p.I >> 2) <= kF2TeamThreads) return launch_fused3_cfg<MODEL, D, 1>(p, grid, smem, st);        \
+    return launch_fused3_cfg<MODEL, D, 2>(p, grid, smem, st);                                          \
   }
 
 }  // namespace vibo
