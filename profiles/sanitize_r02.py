@@ -1,8 +1,8 @@
 """Workload for compute-sanitizer (memcheck / racecheck), round 2:
 
-* the headline single-pass kernel (fused2_kernel, eval and grad, in-kernel noise prologue) on a
-  shape where every team of every CTA walks its stage ring >= 3 laps, plus a ragged last chunk
-  and rows with missing cells;
+* the headline single-pass kernels (fused2_kernel for evaluation and narrow rows, the item-owner
+  fused3_kernel for training with wide rows; in-kernel noise prologue) on shapes where every team
+  of every CTA walks its stage ring >= 3 laps, plus a ragged last chunk and rows with missing cells;
 * the round-2 kernels: step tail / flat Adam / param forward with in-kernel item noise (through
   ShardedElboTrainer's five-launch step), the sample-loop kernels, pack / unpack, the tcgen05
   per-cell MLP, the composed conditional path.
@@ -10,10 +10,11 @@
     compute-sanitizer --tool racecheck python profiles/sanitize_r02.py [fused|rest]
 
 `fused` runs only the single-pass kernels, `rest` everything else (default: both).  With
-VIBO_FUSED_DEBUG=3 the single-pass kernels put a team barrier in front of the stage hand-off (see
-csrc/vibo_fused2_kernel.cuh): racecheck does not credit the production hand-off (mbarrier arrive by
-the reading warps, wait by the refilling warp) as ordering the bulk copy after the reads and reports
-it; with the barrier it reports nothing, i.e. there is no other hazard in those kernels.
+VIBO_FUSED_DEBUG=3 fused2_kernel / fused_uncond_kernel put a team barrier in front of the stage
+hand-off (see csrc/vibo_fused2_kernel.cuh): racecheck does not credit their production hand-off
+(mbarrier arrive by the reading warps, wait by the refilling warp) as ordering the bulk copy after the
+reads and reports it; with the barrier it reports nothing, i.e. there is no other hazard in those
+kernels.  fused3_kernel hands a stage back through the team barrier itself.
 """
 import os
 import sys
@@ -55,6 +56,10 @@ def main_fused():
     fused(148 * 5 * 16 * 10 + 7, 100, 2, 1, 0.1)     # narrow rows (C1's shape), missing cells
     fused(148 * 4 * 8 * 8 + 5, 500, 3, 1, 0.05)      # register-accumulator 3PL kernel
     fused(9000, 96, 2, 2, 0.0)                       # D = 2
+    # item-owner training kernel (fused3_kernel): rows with missing cells (row-by-row path), one item group
+    # per thread (I <= 512), 1PL
+    fused(148 * 5 * 4 * 6 + 2, 1000, 2, 1, 0.08)
+    fused(148 * 5 * 8 * 6 + 5, 500, 1, 1, 0.0)
 
 
 def main_rest():
@@ -80,6 +85,8 @@ def main_rest():
     cr, ck = rows(148 * 16 * 3 + 9, 1000, 0.0, 7)
     ct = ShardedElboTrainer(cm, cuda_graph=False)
     print("conditional", float(ct.train_step(cr, ck).item()))
+    # single-pass conditional evaluation (tcgen05 encode + on-chip bit tile + link warps), ragged last tile
+    print("conditional eval", float(ct.eval_step(cr, ck).item()))
     torch.cuda.synchronize()
 
 

@@ -1,8 +1,9 @@
 """Planar normalizing flows on the (P, D) abilities and (I, F) item features
 (``--n-norm-flows``).  Parameter containers and state_dict keys match the
 reference (src/torch_core/flows.py:6-66: ``flows.{k}.{u,w,b}``, u, w ~ N(0, 1),
-b = 1) so reference checkpoints load; the math is per-person / per-item and
-tiny, so it stays in PyTorch autograd around the kernels.
+b = 1) so reference checkpoints load.  On the GPU the K planar steps and the flow-form
+prior / entropy terms run fused per row (``vibo_flow_person_forward / _backward``) for the
+abilities and for the item features alike; these modules are the autograd fallback.
 """
 import torch
 import torch.nn.functional as F
@@ -51,8 +52,11 @@ class NormalizingFlows(nn.Module):
         return z, total
 
     def stacked_parameters(self):
-        """(uhat (K, D), w (K, D), b (K,)) for the fused per-person kernel."""
-        uhat = torch.stack([planar_uhat(f.u, f.w) for f in self.flows])
+        """(uhat (K, D), w (K, D), b (K,)) for the fused planar-flow kernels; the invertibility
+        correction of all K flows in one batch of elementwise ops (reference flows.py:26-29)."""
+        u = torch.stack([f.u for f in self.flows])
         w = torch.stack([f.w for f in self.flows])
         b = torch.cat([f.b for f in self.flows])
+        uw = (u * w).sum(1, keepdim=True)
+        uhat = u + (F.softplus(uw) - 1.0 - uw) * w / (w * w).sum(1, keepdim=True)
         return uhat, w, b

@@ -486,7 +486,7 @@ class VIBO_1PL(nn.Module):
                                        seed, person_offset, item_term_scale, return_outputs,
                                        float(annealing_factor), kl_form)
         chain = (self.fuse_param_chain and item_feat_mu.is_cuda and not self.conditional_posterior
-                 and self.n_norm_flows == 0 and self.hidden_dim <= 256 and not general)
+                 and self.hidden_dim <= 256 and not general)   # with flows: draw + expert table only
         if chain:
             mlp = self.ability_encoder.mlp
             item_feat, table, item_term_raw = VF.ParamChain.apply(
@@ -503,7 +503,7 @@ class VIBO_1PL(nn.Module):
         if self.n_norm_flows > 0 or general:
             return self._composed_elbo(resp, msk, table, item_feat, item_feat_mu, item_feat_logvar,
                                        eps_ability, seed, person_offset, item_term_scale, return_outputs,
-                                       beta, kl_form)
+                                       beta, kl_form, eps_item=eps_item)
 
         cfg = dict(irt_model=self.irt_num, conditional=self.conditional_posterior,
                    missing_policy=self.ability_encoder.missing_policy,
@@ -536,7 +536,7 @@ class VIBO_1PL(nn.Module):
         return loss
 
     def _composed_elbo(self, resp, msk, table, item_feat, item_feat_mu, item_feat_logvar, eps_ability,
-                       seed, person_offset, item_term_scale, return_outputs, beta, kl_form):
+                       seed, person_offset, item_term_scale, return_outputs, beta, kl_form, eps_item=None):
         """-ELBO composed in autograd around the kernels: ability posterior (encode kernel for the
         product merge, PyTorch reductions / GEMMs on the collapsed table for the mean merge) ->
         draw [-> planar flows, fused per person on the GPU] -> link / log-likelihood kernel ->
@@ -555,8 +555,17 @@ class VIBO_1PL(nn.Module):
         outputs = dict(ability_mu=a_mu, ability_logvar=a_lv, item_feat=item_feat, item_feat_mu=item_feat_mu,
                        item_feat_logvar=item_feat_logvar)
         if self.n_norm_flows > 0:
-            item_k, i_ldj = self.item_norm_flows(item_feat)
-            if resp.is_cuda and self.n_norm_flows <= 8 and isinstance(self.ability_norm_flows.flows[0], PlanarFlow):
+            fused_flows = (resp.is_cuda and self.n_norm_flows <= 8
+                           and isinstance(self.ability_norm_flows.flows[0], PlanarFlow))
+            item = None
+            if fused_flows and eps_item is not None and self.item_feat_dim <= 8:
+                # the item side is the same computation on I rows of width F: draw, K planar flows and
+                # log N(z_K; 0, 1) - log N(z_0; mu, exp lv) + sum_k ldj_k in one kernel each way
+                uhat, fw, fb = self.item_norm_flows.stacked_parameters()
+                _, item_k, item = VF.FlowPerson.apply(item_feat_mu, item_feat_logvar, eps_item, uhat, fw, fb)
+            else:
+                item_k, i_ldj = self.item_norm_flows(item_feat)
+            if fused_flows:
                 # draw + K planar flows + person-side terms in one kernel each way
                 uhat, fw, fb = self.ability_norm_flows.stacked_parameters()
                 ability, ability_k, person = VF.FlowPerson.apply(a_mu, a_lv, eps_ability, uhat, fw, fb)
@@ -566,8 +575,9 @@ class VIBO_1PL(nn.Module):
                 person = standard_normal_log_pdf(ability_k).sum() \
                     - (normal_log_pdf(ability, a_mu, a_lv).sum() - a_ldj.sum())
             ll = self._loglik(resp, msk, ability_k, item_k)
-            item = standard_normal_log_pdf(item_k).sum() \
-                - (normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum() - i_ldj.sum())
+            if item is None:
+                item = standard_normal_log_pdf(item_k).sum() \
+                    - (normal_log_pdf(item_feat, item_feat_mu, item_feat_logvar).sum() - i_ldj.sum())
             loss = -(ll + person + item_term_scale * item)
             outputs.update(ability=ability, ability_k=ability_k, item_feat_k=item_k)
         else:
