@@ -397,8 +397,11 @@ def main():
         achieved = cells * BYTES_PER_CELL / (k_ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(workload_name, mode),
-                "kernel": ("fused2_kernel<GRAD=%s>" % ("true" if mode == "train" else "false"))
-                if tr.uses_fused else "general kernels",
+                "kernel": (("fused3_kernel (item-owner, forward + gradients)"
+                            if mode == "train" and tr.model.num_item >= 384
+                            and os.environ.get("VIBO_DISABLE_FUSED3") != "1"
+                            else "fused2_kernel<GRAD=%s>" % ("true" if mode == "train" else "false"))
+                           if tr.uses_fused else "general kernels"),
                 "kernel_ms": k_ms, "algorithmic_bytes_per_cell": BYTES_PER_CELL, "peak_source": peak_src}
 
     resp, mask, model, trainer = make(args.workload, world, rank, rank * P, seed_rows=42 + rank)

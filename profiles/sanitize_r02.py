@@ -14,7 +14,11 @@ VIBO_FUSED_DEBUG=3 fused2_kernel / fused_uncond_kernel put a team barrier in fro
 hand-off (see csrc/vibo_fused2_kernel.cuh): racecheck does not credit their production hand-off
 (mbarrier arrive by the reading warps, wait by the refilling warp) as ordering the bulk copy after the
 reads and reports it; with the barrier it reports nothing, i.e. there is no other hazard in those
-kernels.  fused3_kernel hands a stage back through the team barrier itself.
+kernels.  fused3_kernel hands a stage back through the team barrier itself and is reported clean as is.
+With VIBO_E5_DEBUG=8 the single-pass conditional evaluation (tc5_eval_kernel) runs its epilogue / packer
+warps and its link warps in lock-step through two 768-thread barriers per tile: the production kernel
+orders their shared-memory hand-offs (theta, flags, bit tile) with mbarrier arrive / wait pairs, which
+racecheck credits for bulk copies but not for ordinary loads and stores; in lock-step it reports nothing.
 """
 import os
 import sys

@@ -528,3 +528,26 @@ def test_forward_only_conditional_vs_oracle(vb, monkeypatch, P, I, D, irt, cond,
                               irt_model=irt, conditional=cond, missing_policy=policy, elbo_form=form,
                               want_grads=False)["scalars"].cpu().numpy()
     assert np.allclose(a, b, rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["owner_train", "owner_train_missing", "conditional_eval"])
+def test_pipeline_kernels_bit_reproducible(vb, kind):
+    """The mbarrier-pipelined kernels (item-owner training kernel; single-pass conditional evaluation)
+    return bit-identical results over repeated launches on a shape with many ring laps per CTA:
+    any unordered shared-memory hand-off between their warp roles would show up as run-to-run noise
+    (compute-sanitizer racecheck cannot see mbarrier arrive / wait ordering)."""
+    if kind == "conditional_eval":
+        P, I, D, irt, cond, miss = 148 * 128 * 3 + 77, 1000, 5, 3, True, 0.0
+    else:
+        P, I, D, irt, cond, miss = 148 * 5 * 4 * 6 + 3, 1000, 1, 2, False, (0.05 if kind.endswith("missing") else 0.0)
+    resp, mask, table, item, eps = _synth(P, I, D, irt, cond, miss, seed=5)
+    dev = "cuda"
+    args = [torch.from_numpy(a).to(dev) for a in (resp, mask, table, item, eps)]
+    outs = []
+    for _ in range(6):
+        o = vb.kernels.fused_elbo(*args, irt_model=irt, conditional=cond, beta=0.9, want_grads=not cond)
+        torch.cuda.synchronize()
+        outs.append({k: v.clone() for k, v in o.items() if isinstance(v, torch.Tensor)})
+    for o in outs[1:]:
+        for k, v in outs[0].items():
+            assert torch.equal(v, o[k]), (kind, k)

@@ -247,12 +247,14 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
   if (tt < 32) reinterpret_cast<float*>(t_cnt)[kF3Tab / 4 + tt] = 0.0f;   // table sums
   __syncthreads();
 
-  // one opaque base per region (a plain cvta result would be re-derived at every use)
-  uint32_t stage0 = smem_u32(t_stage), cnt0 = smem_u32(t_cnt), cst0 = smem_u32(s_max);
+  // one opaque base per region (a plain cvta result would be re-derived at every use); every address below is
+  // base + a non-negative offset (compute-sanitizer mis-tracks an mbarrier wait with a negative immediate)
+  uint32_t stage0 = smem_u32(t_stage), cnt0 = smem_u32(t_cnt), sm0 = smem_u32(smem);
   asm volatile("mov.u32 %0, %0;" : "+r"(stage0));
   asm volatile("mov.u32 %0, %0;" : "+r"(cnt0));
-  asm volatile("mov.u32 %0, %0;" : "+r"(cst0));
-  const uint32_t bar0 = cst0 - (uint32_t)kFusedHdr + (uint32_t)(team * NS) * 8u;   // this team's 'full' barriers
+  asm volatile("mov.u32 %0, %0;" : "+r"(sm0));
+  const uint32_t cst0 = sm0 + (uint32_t)kFusedHdr;                    // s_max
+  const uint32_t bar0 = sm0 + (uint32_t)(team * NS) * 8u;             // this team's 'full' barriers
   const uint32_t tab0 = cnt0 + kF3Tab, half0 = cnt0 + kF3Half, zero0 = cnt0 + kF3Zero, ones0 = cnt0 + kF3Ones;
   const uint32_t sc0 = cst0 + (uint32_t)kF2SumOff;   // s_c; s_max itself is at cst0
   const uint32_t row_x = (uint32_t)I * 4u, row_m = (uint32_t)I;
@@ -317,6 +319,10 @@ __global__ void __launch_bounds__(kF2Threads, 1) fused3_kernel(const __grid_cons
 
   for (int it = 0; it < n_it; ++it) {
     mbar_wait_addr(bar0 + (uint32_t)s * 8, phase);
+    // the grid's ragged last chunk is copied by hand by one warp (ordinary stores, then an mbarrier arrive):
+    // put a team barrier behind the wait as well, once per kernel -- compute-sanitizer racecheck credits
+    // mbarrier waits for bulk copies only, not for ordinary shared-memory stores
+    if (ragged_last && it == n_it - 1) team_barrier(team);
     const uint32_t sb = stage0 + (uint32_t)s * stage_bytes;
     const int rows = (owns_last && it == n_it - 1) ? last_rows : R;
 

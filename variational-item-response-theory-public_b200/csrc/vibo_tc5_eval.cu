@@ -41,7 +41,9 @@ constexpr int kE5ThLd = 8;   // floats per person in the theta tile
 struct E5Params {
   int64_t P;
   int I, n_kb, missing_policy, form;
-  int debug;   // VIBO_E5_DEBUG (attribution runs only): 1 skip the link arithmetic, 2 skip the bit packing, 4 skip the mask scan
+  int debug;   // VIBO_E5_DEBUG (tool runs only): 1 skip the link arithmetic, 2 skip the bit packing, 4 skip the mask scan;
+               // 8: two 768-thread barriers per tile put the epilogue / packer warps and the link warps in lock-step --
+               // racecheck does not credit an mbarrier arrive / wait pair as ordering ordinary shared-memory accesses
   int64_t person_offset;
   const float* resp;
   const uint8_t* mask;
@@ -422,6 +424,10 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       }
       __syncwarp();
       if (lane == 0) bar_arrive(theta_full(b));   // release: theta, flags of this tile
+      if (p.debug & 8) {   // lock-step with the link warps (racecheck runs, see E5Params::debug)
+        asm volatile("bar.sync 3, 768;" ::: "memory");
+        asm volatile("bar.sync 3, 768;" ::: "memory");
+      }
       b ^= 1;
       if (b == 0) aph ^= 1u;
     }
@@ -463,6 +469,10 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       }
       __syncwarp();
       if (lane == 0) bar_arrive(theta_full(b));   // release: the bits of this tile
+      if (p.debug & 8) {   // lock-step with the link warps (racecheck runs, see E5Params::debug)
+        asm volatile("bar.sync 3, 768;" ::: "memory");
+        asm volatile("bar.sync 3, 768;" ::: "memory");
+      }
       b ^= 1;
       if (b == 0) aph ^= 1u;
     }
@@ -505,29 +515,39 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const float* th_tile = s_theta + b * kE5Rows * kE5ThLd;
       const uint8_t* s_flag = s_flags + b * kE5Rows;
       bar_wait(theta_full(b), tph);
+      if (p.debug & 8) asm volatile("bar.sync 3, 768;" ::: "memory");
       f2_t ll2 = pack2(0.0f, 0.0f);
-#pragma unroll 2
-      for (int pr = 0; pr < ((p.debug & 1) ? 0 : kE5Rows); ++pr) {
-        if (s_flag[pr] != 0) continue;   // missing cells (handled by the epilogue) or past the end
-        const float4 t4 = *reinterpret_cast<const float4*>(th_tile + pr * kE5ThLd);
-        const float4 t5 = *reinterpret_cast<const float4*>(th_tile + pr * kE5ThLd + 4);
-        const float tv[8] = {t4.x, t4.y, t4.z, t4.w, t5.x, t5.y, t5.z, t5.w};
-        f2_t z2 = b2;
-        if (MODEL == 1) {
-          z2 = add2(z2, pack2(tv[7], tv[7]));
-        } else {
+      // four persons per trip: one load of their flags and one of each item block's four bit words
+#pragma unroll 1
+      for (int p4 = 0; p4 < ((p.debug & 1) ? 0 : kE5Rows); p4 += 4) {
+        const uint32_t f4 = *reinterpret_cast<const uint32_t*>(s_flag + p4);
+        const uint4 w0 = *reinterpret_cast<const uint4*>(bits + kb0 * kE5Rows + p4);
+        const uint4 w1 = *reinterpret_cast<const uint4*>(bits + kb1 * kE5Rows + p4);
+        const uint32_t wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int d = 0; d < D; ++d) z2 = fma2(pack2(tv[d], tv[d]), na2[d], z2);
+        for (int q = 0; q < 4; ++q) {
+          if ((f4 >> (8 * q)) & 0xffu) continue;   // missing cells (handled by the epilogue) or past the end
+          const float* tp = th_tile + (p4 + q) * kE5ThLd;
+          const float4 t4 = *reinterpret_cast<const float4*>(tp);
+          const float4 t5 = *reinterpret_cast<const float4*>(tp + 4);
+          const float tv[8] = {t4.x, t4.y, t4.z, t4.w, t5.x, t5.y, t5.z, t5.w};
+          f2_t z2 = b2;
+          if (MODEL == 1) {
+            z2 = add2(z2, pack2(tv[7], tv[7]));
+          } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) z2 = fma2(pack2(tv[d], tv[d]), na2[d], z2);
+          }
+          const bool x0 = (wa[q] & lane_bit) != 0, x1 = (wb[q] & lane_bit) != 0;
+          ll2 = fma2(eval_pair<MODEL>(z2, x0, x1, g2, omg2), scale2, ll2);
         }
-        const bool x0 = (bits[kb0 * kE5Rows + pr] & lane_bit) != 0;
-        const bool x1 = (bits[kb1 * kE5Rows + pr] & lane_bit) != 0;
-        ll2 = fma2(eval_pair<MODEL>(z2, x0, x1, g2, omg2), scale2, ll2);
       }
       float l0, l1;
       unpack2(ll2, l0, l1);
       acc_ll += (double)(l0 + l1);
       __syncwarp();
       if (lane == 0) bar_arrive(tile_done(b));
+      if (p.debug & 8) asm volatile("bar.sync 3, 768;" ::: "memory");
       b ^= 1;
       if (b == 0) tph ^= 1u;
     }
