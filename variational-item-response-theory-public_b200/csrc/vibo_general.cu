@@ -190,12 +190,13 @@ __global__ void __launch_bounds__(512) encode_bwd_kernel(int64_t P, int I, const
 // Reduce the per-CTA (A, B) partials in a fixed order and apply the expert
 // chain rule: d/d mu = tau A ; d/d lam = (mu A + B) (-exp(lam) tau^2).
 // Unconditional tables additionally sum over items.
-__global__ void __launch_bounds__(256) encode_bwd_finalize_kernel(int I, int D, int cond, int nparts,
-                                                                  const float* __restrict__ part,
-                                                                  const float* __restrict__ table,
-                                                                  float* __restrict__ g_table) {
-  // block = 32 outputs x 8 slices of the partials, combined through shared memory in a fixed order
-  __shared__ double sa[8][33], sb[8][33];
+constexpr int kSumSlices = 32;   // partial slices per block of the fixed-order reducers (short dependent chains)
+__global__ void __launch_bounds__(32 * kSumSlices) encode_bwd_finalize_kernel(int I, int D, int cond, int nparts,
+                                                                              const float* __restrict__ part,
+                                                                              const float* __restrict__ table,
+                                                                              float* __restrict__ g_table) {
+  // block = 32 outputs x 32 slices of the partials, combined through shared memory in a fixed order
+  __shared__ double sa[kSumSlices][33], sb[kSumSlices][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int It = cond ? I : 1;
   const int n = 2 * It * D;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) encode_bwd_finalize_kernel(int I, int D, 
     jt = (t / D) % It;
     r = t / (D * It);
     const int j0 = cond ? jt : 0, j1 = cond ? jt + 1 : I;
-    for (int p = slice; p < nparts; p += 8) {
+    for (int p = slice; p < nparts; p += kSumSlices) {
       const float* src = part + (size_t)p * 2 * I * 2 * D;
       for (int j = j0; j < j1; ++j) {
         a += src[((size_t)r * I + j) * 2 * D + d];
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256) encode_bwd_finalize_kernel(int I, int D, 
   if (slice == 0 && t < n) {
     double ta = 0.0, tb = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < kSumSlices; ++q) {
       ta += sa[q][lane];
       tb += sb[q][lane];
     }
@@ -353,22 +354,22 @@ __global__ void __launch_bounds__(512) link_kernel(int64_t P, int I, const float
   block_sum_to(ll_acc, part_ll + blockIdx.x);
 }
 
-// out[k] = scale * sum_p part[p][k], fixed order (deterministic).  Block = 32 outputs x 8
-// slices: each thread sums every 8th partial, the slices are combined through shared memory.
-__global__ void __launch_bounds__(256) sum_partials_f32_kernel(const float* __restrict__ part, int nparts, int n,
-                                                               float scale, float* __restrict__ out) {
-  __shared__ double sh[8][33];
+// out[k] = scale * sum_p part[p][k], fixed order (deterministic).  Block = 32 outputs x 32
+// slices: each thread sums every 32nd partial, the slices are combined through shared memory.
+__global__ void __launch_bounds__(32 * kSumSlices) sum_partials_f32_kernel(const float* __restrict__ part, int nparts,
+                                                                           int n, float scale, float* __restrict__ out) {
+  __shared__ double sh[kSumSlices][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
   double s = 0.0;
   if (k < n)
-    for (int p = slice; p < nparts; p += 8) s += part[(size_t)p * n + k];
+    for (int p = slice; p < nparts; p += kSumSlices) s += part[(size_t)p * n + k];
   sh[slice][lane] = s;
   __syncthreads();
   if (slice == 0 && k < n) {
     double t = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += sh[q][lane];
+    for (int q = 0; q < kSumSlices; ++q) t += sh[q][lane];
     out[k] = scale * (float)t;
   }
 }
@@ -527,7 +528,7 @@ static cudaError_t launch_encode_bwd_d(const vibo_desc& d, const float* resp, co
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int n = 2 * (d.conditional ? d.num_item : 1) * D;
-  encode_bwd_finalize_kernel<<<(n + 31) / 32, 256, 0, st>>>(d.num_item, D, d.conditional, grid,
+  encode_bwd_finalize_kernel<<<(n + 31) / 32, 32 * kSumSlices, 0, st>>>(d.num_item, D, d.conditional, grid,
                                                               part, table, g_table);
   note_launch(2);
   return cudaGetLastError();
@@ -556,7 +557,7 @@ static cudaError_t launch_link_dm(const vibo_desc& d, const float* resp, const u
   note_launch(2);
   if (g_item != nullptr) {
     const int n = d.num_item * F;
-    sum_partials_f32_kernel<<<(n + 31) / 32, 256, 0, st>>>(part_g, grid, n, 1.0f, g_item);
+    sum_partials_f32_kernel<<<(n + 31) / 32, 32 * kSumSlices, 0, st>>>(part_g, grid, n, 1.0f, g_item);
     note_launch();
   }
   return cudaGetLastError();
@@ -598,7 +599,7 @@ cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8
     if (e != cudaSuccess) return e;
     const int n = 2 * (d.conditional ? d.num_item : 1) * d.ability_dim;
     // the stream kernel already summed over items for the unconditional table
-    encode_bwd_finalize_kernel<<<(n + 31) / 32, 256, 0, st>>>(d.conditional ? d.num_item : 1, d.ability_dim,
+    encode_bwd_finalize_kernel<<<(n + 31) / 32, 32 * kSumSlices, 0, st>>>(d.conditional ? d.num_item : 1, d.ability_dim,
                                                                 d.conditional, grid, part, table, g_table);
     note_launch(2);
     return cudaGetLastError();
@@ -623,7 +624,7 @@ cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* ma
     note_launch(2);
     if (g_item != nullptr) {
       const int n = d.num_item * item_width_host(d.irt_model, d.ability_dim);
-      sum_partials_f32_kernel<<<(n + 31) / 32, 256, 0, st>>>(part_g, grid, n, 1.0f, g_item);
+      sum_partials_f32_kernel<<<(n + 31) / 32, 32 * kSumSlices, 0, st>>>(part_g, grid, n, 1.0f, g_item);
       note_launch();
     }
     return cudaGetLastError();

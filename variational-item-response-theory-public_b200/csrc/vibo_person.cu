@@ -320,17 +320,28 @@ __global__ void __launch_bounds__(256) flow_person_backward_kernel(int64_t P, in
   }
 }
 
-// out[k] = sum_p part[p][k] for the flow parameter gradients (n small), fixed order
-__global__ void flow_sum_kernel(const float* __restrict__ part, int nparts, int n, int D, int K,
-                                float* __restrict__ g_uhat, float* __restrict__ g_w, float* __restrict__ g_b) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
+// out[k] = sum_p part[p][k] for the flow parameter gradients (n small): one block per output, strided
+// partial sums then a shared-memory tree in a fixed order (deterministic)
+__global__ void __launch_bounds__(128) flow_sum_kernel(const float* __restrict__ part, int nparts, int n, int D, int K,
+                                                       float* __restrict__ g_uhat, float* __restrict__ g_w,
+                                                       float* __restrict__ g_b) {
+  __shared__ double sh[128];
+  const int t = blockIdx.x;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * n + t];
-  const int k = t / (2 * D + 1), r = t % (2 * D + 1);
-  if (r < D) g_uhat[k * D + r] = (float)s;
-  else if (r < 2 * D) g_w[k * D + (r - D)] = (float)s;
-  else g_b[k] = (float)s;
+  for (int p = threadIdx.x; p < nparts; p += 128) s += part[(size_t)p * n + t];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float v = (float)sh[0];
+    const int k = t / (2 * D + 1), r = t % (2 * D + 1);
+    if (r < D) g_uhat[k * D + r] = v;
+    else if (r < 2 * D) g_w[k * D + (r - D)] = v;
+    else g_b[k] = v;
+  }
 }
 
 int flow_grid(int64_t P) {
@@ -367,7 +378,7 @@ cudaError_t launch_flow_person_backward(int64_t P, int D, int K, const float* am
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int n = K * (2 * D + 1);
-  flow_sum_kernel<<<(n + 127) / 128, 128, 0, st>>>(part_g, grid, n, D, K, g_uhat, g_w, g_b);
+  flow_sum_kernel<<<n, 128, 0, st>>>(part_g, grid, n, D, K, g_uhat, g_w, g_b);
   note_launch(2);
   return cudaGetLastError();
 }
