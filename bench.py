@@ -473,11 +473,19 @@ def main():
         ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        # bytes that cross PCIe: the share of every chunk that the library's host thread pool packs to
+        # 1 B/cell inside the timed region goes as 1 B/cell, the rest in the reference layout
+        chunk = getattr(model, "host_chunk_person", 65536)
+        share = float(lib.vibo_host_pack_share(ctypes.byref(vibo_b200.kernels.make_desc(Pe, I, D, irt, cond)),
+                                               ctypes.c_int64(chunk)))
         e2e = {"value": Pe * I * world * ksteps / (float(ems.item()) * 1e-3), "unit": "cells/s",
-               "h2d_bytes_per_step": Pe * I * BYTES_PER_CELL, "d2h_bytes_per_step": 16,
+               "h2d_bytes_per_step": int(Pe * I * ((1.0 - share) * BYTES_PER_CELL + share)), "d2h_bytes_per_step": 16,
+               "host_input_bytes_per_step": Pe * I * BYTES_PER_CELL, "host_packed_share": share,
+               "host_threads": int(lib.vibo_host_threads()),
                "rows_per_step": Pe, "steps": ksteps, "ms_per_step": float(ems.item()) / ksteps,
-               "note": "pinned host response/mask (reference layout, 5 B/cell) -> vibo_fused_elbo_host "
-                       "(chunked H2D overlapped with the kernel) -> loss read back"}
+               "note": "pinned host response/mask (reference layout, 5 B/cell) -> vibo_fused_elbo_host: per chunk, "
+                       "host_packed_share of the rows is packed to 1 B/cell by the library's host threads while the "
+                       "rest crosses PCIe as is; H2D overlapped with the kernel of the previous chunk -> loss read back"}
         del resp_h, mask_h
         # the same call with the rows pre-packed on the host (1 B/cell: -1 missing / 0 / 1, packed once
         # at dataset load): PCIe carries 5x fewer bytes; each chunk is expanded on the device

@@ -134,6 +134,15 @@ int vibo_philox_normal(const vibo_desc* desc, uint64_t seed, const uint64_t* see
  * returning.  staging: device scratch of vibo_host_staging_bytes() bytes.
  */
 size_t vibo_host_staging_bytes(const vibo_desc* desc, int64_t chunk_person);
+/*
+ * Host-compressed route of vibo_fused_elbo_host: for chunks of >= 2^20 cells, a share of every chunk's
+ * rows (vibo_host_pack_share(): 0.72 by default, VIBO_HOST_PACK_FRACTION overrides, 0 with fewer than
+ * 4 host threads) is packed to 1 B/cell by the library's host thread pool while the rest of the chunk
+ * is in flight over PCIe in the reference layout, then sent and expanded on the device.  The two routes
+ * use different resources (CPU cores + host DRAM vs the PCIe link), so their throughputs add; results are
+ * identical.  Requires 0 / 1 responses where observed (the Bernoulli model of this path).
+ */
+double vibo_host_pack_share(const vibo_desc* desc, int64_t chunk_person);
 int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
                          const uint8_t* mask_host, const float* table, const float* item_feat,
                          const float* eps_ability, uint64_t seed, float beta,
@@ -146,11 +155,17 @@ int vibo_fused_elbo_host(const vibo_desc* desc, const float* response_host,
  * Packed row format: one signed byte per cell, -1 = missing (src/config.py:14), 0 / 1 = observed
  * response -- the (response, mask) pair of src/datasets.py:928-940 in 1 byte instead of 5.
  *   vibo_pack / vibo_unpack   device-side conversion between the pair and the packed rows (P, I).
+ *   vibo_pack_host            the same conversion of HOST rows on the caller's CPU cores (a pool of
+ *       vibo_host_threads() threads: hardware concurrency, VIBO_HOST_THREADS overrides) -- the
+ *       one-off step at dataset load for the packed entry point below.
  *   vibo_fused_elbo_host_packed   vibo_fused_elbo_host with the rows in HOST memory in the packed
  *       format: PCIe carries 1 B/cell; each chunk is expanded on the device (one streaming kernel)
  *       before the row kernels read it.  Same staging size query (vibo_host_staging_bytes).
  */
 int vibo_pack(const vibo_desc* desc, const float* response, const uint8_t* mask, int8_t* packed, void* stream);
+int vibo_pack_host(const vibo_desc* desc, const float* response_host, const uint8_t* mask_host,
+                   int8_t* packed_host);
+int vibo_host_threads(void);
 int vibo_unpack(const vibo_desc* desc, const int8_t* packed, float* response, uint8_t* mask, void* stream);
 int vibo_fused_elbo_host_packed(const vibo_desc* desc, const int8_t* packed_host, const float* table,
                                 const float* item_feat, const float* eps_ability, uint64_t seed,

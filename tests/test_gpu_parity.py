@@ -324,6 +324,25 @@ def test_host_buffer_entry_matches_device_entry(vb):
     assert rel_l2(out["g_table"].cpu().numpy(), dev["g_table"]) < 1e-5
 
 
+@pytest.mark.parametrize("fraction", [None, "0", "0.37", "1"])
+def test_host_buffer_entry_host_compressed_route(vb, monkeypatch, fraction):
+    """Chunks large enough for the host-compressed route of vibo_fused_elbo_host: part of every chunk
+    is packed to 1 B/cell by the host thread pool while the rest crosses PCIe in the reference layout
+    (default share, DMA only, an odd share, everything packed) -- same result as the device entry."""
+    if fraction is not None:
+        monkeypatch.setenv("VIBO_HOST_PACK_FRACTION", fraction)
+    P, I, D = 40003, 200, 1
+    resp, mask, table, item, eps = _synth(P, I, D, 2, False, 0.1, seed=23)
+    dev = _run_fused(vb, resp, mask, table, item, eps, irt_model=2, conditional=False)
+    out = vb.kernels.fused_elbo_host(torch.from_numpy(resp).pin_memory(), torch.from_numpy(mask).pin_memory(),
+                                     torch.from_numpy(table).cuda(), torch.from_numpy(item).cuda(),
+                                     torch.from_numpy(eps).cuda(), irt_model=2, conditional=False,
+                                     chunk_person=8192)
+    assert rel_l2(out["scalars_host"].numpy(), dev["scalars"]) < 1e-6
+    assert rel_l2(out["g_item"].cpu().numpy(), dev["g_item"]) < 1e-5
+    assert rel_l2(out["g_table"].cpu().numpy(), dev["g_table"]) < 1e-5
+
+
 def test_missing_row_edge_cases(vb):
     """A fully missing row: prior experts only -> N(0, 1/I) posterior mean 0;
     under --drop-missing the reference divides 0/0 (NaN) and so do we

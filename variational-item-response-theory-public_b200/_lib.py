@@ -72,6 +72,9 @@ SIGNATURES = {
     "vibo_flow_person_backward": (C.c_int, [_PD, C.c_int] + [_p] * 13 + [_p, C.c_size_t, _p]),
     "vibo_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), _p]),
     "vibo_comm_connect": (C.c_int, [_p, _p]),
+    "vibo_pack_host": (C.c_int, [_p, _p, _p, _p]),
+    "vibo_host_threads": (C.c_int, []),
+    "vibo_host_pack_share": (C.c_double, [_p, C.c_int64]),
     "vibo_comm_allreduce": (C.c_int, [_p, _p, C.c_size_t, _p]),
     "vibo_comm_allreduce_adam": (C.c_int, [_p, _p, C.c_size_t, C.c_size_t, _p, _p, _p, _p, C.c_float, C.c_float,
                                            C.c_float, C.c_float, _p]),
@@ -98,6 +101,15 @@ def load():
             f"{LIB_PATH} not found: the CUDA extension is not built. Run "
             "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
             "There is no CPU or PyTorch fallback for the VIBO kernels.")
+    # one process per GPU: share the host cores between the ranks of this node (the library's host
+    # thread pool, used by the host-buffer entry points, reads VIBO_HOST_THREADS when it starts)
+    if "VIBO_HOST_THREADS" not in os.environ:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        os.environ["VIBO_HOST_THREADS"] = str(max(1, cores // local))
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

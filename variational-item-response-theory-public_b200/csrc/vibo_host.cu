@@ -5,6 +5,7 @@
 // (src/datasets.py:928-940) uses.
 #include <string>
 
+#include "vibo_hostpack.h"
 #include "vibo_kernels.h"
 
 namespace {
@@ -16,6 +17,11 @@ struct HostPipe {
   cudaEvent_t copied[2] = {nullptr, nullptr};
   cudaEvent_t consumed[2] = {nullptr, nullptr};
   cudaEvent_t start = nullptr;
+  // host-compressed route: pinned landing buffers of the CPU packers and the events of their H2D copies
+  static constexpr int kPackBufs = 3;
+  int8_t* pack_host[kPackBufs] = {nullptr, nullptr, nullptr};
+  size_t pack_cap = 0;
+  cudaEvent_t pack_sent[kPackBufs] = {nullptr, nullptr, nullptr};
   int device = -1;
   cudaError_t ensure() {
     int dev = 0;
@@ -28,9 +34,37 @@ struct HostPipe {
       if ((e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)) != cudaSuccess) return e;
       if ((e = cudaEventCreateWithFlags(&consumed[i], cudaEventDisableTiming)) != cudaSuccess) return e;
     }
+    for (int i = 0; i < kPackBufs; ++i)
+      if ((e = cudaEventCreateWithFlags(&pack_sent[i], cudaEventDisableTiming)) != cudaSuccess) return e;
     return cudaEventCreateWithFlags(&start, cudaEventDisableTiming);
   }
+  cudaError_t ensure_pack(size_t bytes) {
+    if (bytes <= pack_cap) return cudaSuccess;
+    for (int i = 0; i < kPackBufs; ++i) {
+      if (pack_host[i] != nullptr) cudaFreeHost(pack_host[i]);
+      pack_host[i] = nullptr;
+    }
+    pack_cap = 0;
+    for (int i = 0; i < kPackBufs; ++i) {
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&pack_host[i]), bytes, cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+    }
+    pack_cap = bytes;
+    return cudaSuccess;
+  }
 };
+
+// Share of every chunk's rows that crosses PCIe host-compressed (packed to 1 B/cell by the host thread pool
+// while the rest of the chunk is in flight in the reference layout).  The two routes use different resources
+// (CPU cores + host DRAM vs the PCIe link), so their rates add: with ~90 GB/s of packing (16 cores) and
+// ~51 GB/s of DMA the optimum is ~0.73.  VIBO_HOST_PACK_FRACTION overrides; 0 = DMA only.
+double host_pack_fraction(size_t chunk_cells) {
+  double f = 0.72;
+  if (const char* e = getenv("VIBO_HOST_PACK_FRACTION")) f = atof(e);
+  if (vibo::host_pool_threads() < 4 && getenv("VIBO_HOST_PACK_FRACTION") == nullptr) f = 0.0;   // too few cores to help
+  if (chunk_cells < (1u << 20)) f = 0.0;   // tiny chunks: not worth the synchronisation
+  return f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f);
+}
 thread_local HostPipe g_pipe;
 
 struct StagingLayout {
@@ -109,22 +143,52 @@ static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_hos
   VIBO_HOST_CUDA(cudaEventRecord(g_pipe.start, st), "event record");
   VIBO_HOST_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.start, 0), "stream wait");
 
+  const double pack_f = packed ? 0.0 : host_pack_fraction((size_t)(d.num_person < chunk_person ? d.num_person : chunk_person) * d.num_item);
+  if (pack_f > 0.0)
+    VIBO_HOST_CUDA(g_pipe.ensure_pack((size_t)((double)chunk_person * pack_f + 1.0) * d.num_item), "pinned pack buffers");
   int64_t c = 0;
   for (int64_t r0 = 0; r0 < d.num_person; r0 += chunk_person, ++c) {
     const int b = (int)(c & 1);
     const int64_t n = (d.num_person - r0 < chunk_person) ? d.num_person - r0 : chunk_person;
     if (c >= 2) VIBO_HOST_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.consumed[b], 0), "stream wait");
+    int64_t unpack_cells = 0;
+    size_t unpack_first = 0;
     if (packed) {
       VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.packed[b], packed_host + (size_t)r0 * d.num_item,
                                      (size_t)n * d.num_item, cudaMemcpyHostToDevice, g_pipe.copy),
                      "H2D copy of packed rows");
     } else {
-      VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.resp[b], response_host + (size_t)r0 * d.num_item,
-                                     (size_t)n * d.num_item * sizeof(float), cudaMemcpyHostToDevice, g_pipe.copy),
-                     "H2D copy of response rows");
-      VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item, (size_t)n * d.num_item,
-                                     cudaMemcpyHostToDevice, g_pipe.copy),
-                     "H2D copy of mask rows");
+      // rows [0, n_raw) of the chunk in the reference layout by DMA; rows [n_raw, n) packed on the host
+      // (while that DMA runs) and sent as 1 B/cell
+      int64_t n_raw = n;
+      if (pack_f > 0.0) {   // the raw part is a multiple of 16 rows: the unpacked rows behind it stay 16-byte aligned
+        n_raw = (n - (int64_t)((double)n * pack_f) + 15) / 16 * 16;
+        if (pack_f >= 1.0) n_raw = 0;
+        if (n_raw > n) n_raw = n;
+      }
+      const int64_t n_pack = n - n_raw;
+      if (n_raw > 0) {
+        VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.resp[b], response_host + (size_t)r0 * d.num_item,
+                                       (size_t)n_raw * d.num_item * sizeof(float), cudaMemcpyHostToDevice,
+                                       g_pipe.copy),
+                       "H2D copy of response rows");
+        VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item,
+                                       (size_t)n_raw * d.num_item, cudaMemcpyHostToDevice, g_pipe.copy),
+                       "H2D copy of mask rows");
+      }
+      if (n_pack > 0) {
+        const int hb = (int)(c % HostPipe::kPackBufs);
+        const size_t cells = (size_t)n_pack * d.num_item, first = (size_t)(r0 + n_raw) * d.num_item;
+        if (c >= HostPipe::kPackBufs)   // the copy that last read this pinned buffer
+          VIBO_HOST_CUDA(cudaEventSynchronize(g_pipe.pack_sent[hb]), "event synchronize");
+        vibo::host_pack_parallel(response_host + first, mask_host + first, g_pipe.pack_host[hb], cells);
+        VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.packed[b], g_pipe.pack_host[hb], cells, cudaMemcpyHostToDevice,
+                                       g_pipe.copy),
+                       "H2D copy of host-packed rows");
+        VIBO_HOST_CUDA(cudaEventRecord(g_pipe.pack_sent[hb], g_pipe.copy), "event record");
+        unpack_cells = (int64_t)cells;
+        unpack_first = (size_t)n_raw * d.num_item;
+      }
     }
     VIBO_HOST_CUDA(cudaEventRecord(g_pipe.copied[b], g_pipe.copy), "event record");
     VIBO_HOST_CUDA(cudaStreamWaitEvent(st, g_pipe.copied[b], 0), "stream wait");
@@ -132,6 +196,11 @@ static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_hos
       VIBO_HOST_CUDA(vibo::launch_unpack(n * d.num_item, reinterpret_cast<const int8_t*>(base + L.packed[b]),
                                          reinterpret_cast<float*>(base + L.resp[b]),
                                          reinterpret_cast<uint8_t*>(base + L.mask[b]), st),
+                     "unpack");
+    else if (unpack_cells > 0)
+      VIBO_HOST_CUDA(vibo::launch_unpack(unpack_cells, reinterpret_cast<const int8_t*>(base + L.packed[b]),
+                                         reinterpret_cast<float*>(base + L.resp[b]) + unpack_first,
+                                         reinterpret_cast<uint8_t*>(base + L.mask[b]) + unpack_first, st),
                      "unpack");
     vibo_desc dc = d;
     dc.num_person = n;
@@ -194,6 +263,23 @@ int vibo_pack(const vibo_desc* desc, const float* response, const uint8_t* mask,
                         static_cast<cudaStream_t>(stream)) != cudaSuccess)
     return vibo::set_last_error(VIBO_ERR_CUDA, "vibo_pack: launch failed");
   return VIBO_OK;
+}
+
+int vibo_pack_host(const vibo_desc* desc, const float* response_host, const uint8_t* mask_host,
+                   int8_t* packed_host) {
+  if (desc == nullptr || response_host == nullptr || mask_host == nullptr || packed_host == nullptr ||
+      desc->num_person < 0 || desc->num_item <= 0)
+    return vibo::set_last_error(VIBO_ERR_BAD_ARGUMENT, "vibo_pack_host: bad argument");
+  vibo::host_pack_parallel(response_host, mask_host, packed_host, (size_t)desc->num_person * desc->num_item);
+  return VIBO_OK;
+}
+
+int vibo_host_threads(void) { return vibo::host_pool_threads(); }
+
+double vibo_host_pack_share(const vibo_desc* desc, int64_t chunk_person) {
+  if (desc == nullptr || chunk_person <= 0) return 0.0;
+  const int64_t rows = desc->num_person < chunk_person ? desc->num_person : chunk_person;
+  return host_pack_fraction((size_t)rows * desc->num_item);
 }
 
 int vibo_unpack(const vibo_desc* desc, const int8_t* packed, float* response, uint8_t* mask, void* stream) {

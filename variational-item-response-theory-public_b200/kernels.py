@@ -406,10 +406,16 @@ def unpack_rows(packed):
 def pack_rows_host(response, mask):
     """Host-side packing of dataset arrays (done once at load): (P, I[, 1]) response + mask ->
     pinned (P, I) int8 in the packed row format."""
-    r = response.reshape(response.shape[0], response.shape[1])
-    m = mask.reshape(mask.shape[0], mask.shape[1]) != 0
-    out = torch.where(m, (r > 0.5).to(torch.int8), torch.full((), -1, dtype=torch.int8))
-    return out.contiguous().pin_memory() if torch.cuda.is_available() else out.contiguous()
+    r = response.reshape(response.shape[0], response.shape[1]).contiguous().float()
+    m = mask.reshape(mask.shape[0], mask.shape[1])
+    m = (m if m.dtype == torch.uint8 else (m != 0).to(torch.uint8)).contiguous()
+    out = torch.empty(r.shape, dtype=torch.int8)
+    if torch.cuda.is_available():
+        out = out.pin_memory()
+    desc = make_desc(r.shape[0], r.shape[1], 1, 2, False)
+    # the library's host thread pool (vibo_pack_host): ~100 GB/s of rows on 16 cores
+    _lib.check(_lib.load().vibo_pack_host(C.byref(desc), _ptr(r), _ptr(m), _ptr(out)), "vibo_pack_host")
+    return out
 
 
 def percell_mlp(u, v, z, w0, w2, c2, w4, c4=0.0):
