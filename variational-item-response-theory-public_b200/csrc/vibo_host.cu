@@ -22,6 +22,8 @@ struct HostPipe {
   int8_t* pack_host[kPackBufs] = {nullptr, nullptr, nullptr};
   size_t pack_cap = 0;
   cudaEvent_t pack_sent[kPackBufs] = {nullptr, nullptr, nullptr};
+  cudaEvent_t raw_sent = nullptr;   // behind the raw part of the current chunk (share controller)
+  double share = -1.0;              // current host-packed share of a chunk (< 0: not initialised)
   int device = -1;
   cudaError_t ensure() {
     int dev = 0;
@@ -36,6 +38,7 @@ struct HostPipe {
     }
     for (int i = 0; i < kPackBufs; ++i)
       if ((e = cudaEventCreateWithFlags(&pack_sent[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&raw_sent, cudaEventDisableTiming)) != cudaSuccess) return e;
     return cudaEventCreateWithFlags(&start, cudaEventDisableTiming);
   }
   cudaError_t ensure_pack(size_t bytes) {
@@ -54,17 +57,6 @@ struct HostPipe {
   }
 };
 
-// Share of every chunk's rows that crosses PCIe host-compressed (packed to 1 B/cell by the host thread pool
-// while the rest of the chunk is in flight in the reference layout).  The two routes use different resources
-// (CPU cores + host DRAM vs the PCIe link), so their rates add: with ~90 GB/s of packing (16 cores) and
-// ~51 GB/s of DMA the optimum is ~0.73.  VIBO_HOST_PACK_FRACTION overrides; 0 = DMA only.
-double host_pack_fraction(size_t chunk_cells) {
-  double f = 0.72;
-  if (const char* e = getenv("VIBO_HOST_PACK_FRACTION")) f = atof(e);
-  if (vibo::host_pool_threads() < 4 && getenv("VIBO_HOST_PACK_FRACTION") == nullptr) f = 0.0;   // too few cores to help
-  if (chunk_cells < (1u << 20)) f = 0.0;   // tiny chunks: not worth the synchronisation
-  return f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f);
-}
 thread_local HostPipe g_pipe;
 
 struct StagingLayout {
@@ -88,6 +80,37 @@ StagingLayout staging_layout(const vibo_desc& d, int64_t chunk) {
   L.g_item = off; off += align_up(4 * (size_t)d.num_item * F, 256);
   L.total = off;
   return L;
+}
+
+// Share of every chunk's rows that crosses PCIe host-compressed (packed to 1 B/cell by the host thread pool
+// while the rest of the chunk is in flight in the reference layout).  The two routes use different resources
+// (CPU cores + host DRAM vs the PCIe link), so their rates add: with C GB/s of packing and B GB/s of DMA the
+// balance is share = 5 C / (5 B + 4 C) (~0.73 for 90 and 51 GB/s).  The share starts at 0.72 and follows the
+// machine: after packing a chunk, if the DMA engine has already drained the chunk's raw part it was starved
+// (the CPU route is the slower one: less packing), otherwise it is the bottleneck (more packing).
+// VIBO_HOST_PACK_FRACTION fixes the share; 0 = DMA only.
+constexpr double kShareInit = 0.72, kShareStep = 0.02, kShareMin = 0.2, kShareMax = 0.92;
+bool host_pack_fixed(double* f) {
+  const char* e = getenv("VIBO_HOST_PACK_FRACTION");
+  if (e == nullptr) return false;
+  const double v = atof(e);
+  *f = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+  return true;
+}
+double host_pack_fraction(size_t chunk_cells) {
+  if (chunk_cells < (1u << 20)) return 0.0;   // tiny chunks: not worth the synchronisation
+  double f;
+  if (host_pack_fixed(&f)) return f;
+  if (vibo::host_pool_threads() < 4) return 0.0;   // too few cores to help
+  if (g_pipe.share < 0.0) g_pipe.share = kShareInit;
+  return g_pipe.share;
+}
+void host_pack_feedback(bool dma_starved) {
+  double f;
+  if (host_pack_fixed(&f) || g_pipe.share < 0.0) return;
+  g_pipe.share += dma_starved ? -kShareStep : kShareStep;
+  if (g_pipe.share < kShareMin) g_pipe.share = kShareMin;
+  if (g_pipe.share > kShareMax) g_pipe.share = kShareMax;
 }
 
 }  // namespace
@@ -143,9 +166,10 @@ static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_hos
   VIBO_HOST_CUDA(cudaEventRecord(g_pipe.start, st), "event record");
   VIBO_HOST_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.start, 0), "stream wait");
 
-  const double pack_f = packed ? 0.0 : host_pack_fraction((size_t)(d.num_person < chunk_person ? d.num_person : chunk_person) * d.num_item);
-  if (pack_f > 0.0)
-    VIBO_HOST_CUDA(g_pipe.ensure_pack((size_t)((double)chunk_person * pack_f + 1.0) * d.num_item), "pinned pack buffers");
+  const size_t chunk_cells = (size_t)(d.num_person < chunk_person ? d.num_person : chunk_person) * d.num_item;
+  const bool pack_route = !packed && host_pack_fraction(chunk_cells) > 0.0;
+  if (pack_route)   // sized for the largest share the controller can reach
+    VIBO_HOST_CUDA(g_pipe.ensure_pack((size_t)chunk_person * d.num_item), "pinned pack buffers");
   int64_t c = 0;
   for (int64_t r0 = 0; r0 < d.num_person; r0 += chunk_person, ++c) {
     const int b = (int)(c & 1);
@@ -160,6 +184,7 @@ static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_hos
     } else {
       // rows [0, n_raw) of the chunk in the reference layout by DMA; rows [n_raw, n) packed on the host
       // (while that DMA runs) and sent as 1 B/cell
+      const double pack_f = pack_route ? host_pack_fraction(chunk_cells) : 0.0;   // follows the controller
       int64_t n_raw = n;
       if (pack_f > 0.0) {   // the raw part is a multiple of 16 rows: the unpacked rows behind it stay 16-byte aligned
         n_raw = (n - (int64_t)((double)n * pack_f) + 15) / 16 * 16;
@@ -175,6 +200,7 @@ static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_hos
         VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.mask[b], mask_host + (size_t)r0 * d.num_item,
                                        (size_t)n_raw * d.num_item, cudaMemcpyHostToDevice, g_pipe.copy),
                        "H2D copy of mask rows");
+        if (n_pack > 0) VIBO_HOST_CUDA(cudaEventRecord(g_pipe.raw_sent, g_pipe.copy), "event record");
       }
       if (n_pack > 0) {
         const int hb = (int)(c % HostPipe::kPackBufs);
@@ -182,6 +208,7 @@ static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_hos
         if (c >= HostPipe::kPackBufs)   // the copy that last read this pinned buffer
           VIBO_HOST_CUDA(cudaEventSynchronize(g_pipe.pack_sent[hb]), "event synchronize");
         vibo::host_pack_parallel(response_host + first, mask_host + first, g_pipe.pack_host[hb], cells);
+        if (n_raw > 0 && c >= 1) host_pack_feedback(cudaEventQuery(g_pipe.raw_sent) == cudaSuccess);
         VIBO_HOST_CUDA(cudaMemcpyAsync(base + L.packed[b], g_pipe.pack_host[hb], cells, cudaMemcpyHostToDevice,
                                        g_pipe.copy),
                        "H2D copy of host-packed rows");
