@@ -136,8 +136,8 @@ int vibo_philox_normal(const vibo_desc* desc, uint64_t seed, const uint64_t* see
 size_t vibo_host_staging_bytes(const vibo_desc* desc, int64_t chunk_person);
 /*
  * Host-compressed route of vibo_fused_elbo_host: for chunks of >= 2^20 cells, a share of every chunk's
- * rows (vibo_host_pack_share(): 0.72 by default, VIBO_HOST_PACK_FRACTION overrides, 0 with fewer than
- * 4 host threads) is packed to 1 B/cell by the library's host thread pool while the rest of the chunk
+ * rows (vibo_host_pack_share(): starts at 0.72 and follows the machine, VIBO_HOST_PACK_FRACTION fixes it,
+ * 0 with fewer than 6 host threads per process) is packed to 1 B/cell by the library's host thread pool while the rest of the chunk
  * is in flight over PCIe in the reference layout, then sent and expanded on the device.  The two routes
  * use different resources (CPU cores + host DRAM vs the PCIe link), so their throughputs add; results are
  * identical.  Requires 0 / 1 responses where observed (the Bernoulli model of this path).

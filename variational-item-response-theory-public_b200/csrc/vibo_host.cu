@@ -24,6 +24,8 @@ struct HostPipe {
   cudaEvent_t pack_sent[kPackBufs] = {nullptr, nullptr, nullptr};
   cudaEvent_t raw_sent = nullptr;   // behind the raw part of the current chunk (share controller)
   double share = -1.0;              // current host-packed share of a chunk (< 0: not initialised)
+  int at_floor = 0;                 // consecutive feedbacks with the share at its floor
+  int rest_calls = 0;               // calls left during which the route stays off (it did not pay)
   int device = -1;
   cudaError_t ensure() {
     int dev = 0;
@@ -89,7 +91,11 @@ StagingLayout staging_layout(const vibo_desc& d, int64_t chunk) {
 // machine: after packing a chunk, if the DMA engine has already drained the chunk's raw part it was starved
 // (the CPU route is the slower one: less packing), otherwise it is the bottleneck (more packing).
 // VIBO_HOST_PACK_FRACTION fixes the share; 0 = DMA only.
+// When the host DRAM, not the link, is the shared bottleneck (several GPUs fed from one host) packing cannot win:
+// it reads the same 5 B/cell and adds the packed copy.  The route therefore needs >= 6 pool threads per process,
+// and if the controller stays pinned at the floor it switches the route off for the next 16 calls.
 constexpr double kShareInit = 0.72, kShareStep = 0.02, kShareMin = 0.2, kShareMax = 0.92;
+constexpr int kShareMinThreads = 6, kFloorPatience = 24, kRestCalls = 16;
 bool host_pack_fixed(double* f) {
   const char* e = getenv("VIBO_HOST_PACK_FRACTION");
   if (e == nullptr) return false;
@@ -101,7 +107,8 @@ double host_pack_fraction(size_t chunk_cells) {
   if (chunk_cells < (1u << 20)) return 0.0;   // tiny chunks: not worth the synchronisation
   double f;
   if (host_pack_fixed(&f)) return f;
-  if (vibo::host_pool_threads() < 4) return 0.0;   // too few cores to help
+  if (vibo::host_pool_threads() < kShareMinThreads) return 0.0;   // too few cores per GPU to help
+  if (g_pipe.rest_calls > 0) return 0.0;
   if (g_pipe.share < 0.0) g_pipe.share = kShareInit;
   return g_pipe.share;
 }
@@ -109,8 +116,17 @@ void host_pack_feedback(bool dma_starved) {
   double f;
   if (host_pack_fixed(&f) || g_pipe.share < 0.0) return;
   g_pipe.share += dma_starved ? -kShareStep : kShareStep;
-  if (g_pipe.share < kShareMin) g_pipe.share = kShareMin;
   if (g_pipe.share > kShareMax) g_pipe.share = kShareMax;
+  if (g_pipe.share <= kShareMin) {
+    g_pipe.share = kShareMin;
+    if (++g_pipe.at_floor >= kFloorPatience) {   // the CPU route keeps losing: stop for a while, then probe again
+      g_pipe.at_floor = 0;
+      g_pipe.rest_calls = kRestCalls;
+      g_pipe.share = 0.3;
+    }
+  } else {
+    g_pipe.at_floor = 0;
+  }
 }
 
 }  // namespace
@@ -167,6 +183,7 @@ static int fused_elbo_host_impl(const vibo_desc* desc, const float* response_hos
   VIBO_HOST_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.start, 0), "stream wait");
 
   const size_t chunk_cells = (size_t)(d.num_person < chunk_person ? d.num_person : chunk_person) * d.num_item;
+  if (!packed && g_pipe.rest_calls > 0 && chunk_cells >= (1u << 20)) --g_pipe.rest_calls;
   const bool pack_route = !packed && host_pack_fraction(chunk_cells) > 0.0;
   if (pack_route)   // sized for the largest share the controller can reach
     VIBO_HOST_CUDA(g_pipe.ensure_pack((size_t)chunk_person * d.num_item), "pinned pack buffers");
