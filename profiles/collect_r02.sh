@@ -11,6 +11,7 @@ timeout 900 python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err
 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > $O/${T}_bench_reference.json 2>> $O/${T}_bench.err
 timeout 600 python profiles/kernel_bench.py > $O/${T}_kernel_bench.json 2>> $O/${T}_bench.err
 timeout 600 python profiles/epoch_time.py 2>> $O/${T}_bench.err | grep '^{' > $O/${T}_epoch_time.jsonl
+timeout 300 python profiles/host_pack_bench.py > $O/${T}_host_pack.log 2>> $O/${T}_bench.err
 # launch lists (kernel shares of a step)
 for w in c4 c2 c3 c5; do
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/${T}_launches_$w.csv \

@@ -20,6 +20,7 @@ warps and its link warps in lock-step through two 768-thread barriers per tile: 
 orders their shared-memory hand-offs (theta, flags, bit tile) with mbarrier arrive / wait pairs, which
 racecheck credits for bulk copies but not for ordinary loads and stores; in lock-step it reports nothing.
 """
+import ctypes as C
 import os
 import sys
 
@@ -79,6 +80,14 @@ def main_rest():
     a, b = K.unpack_rows(pk)
     with torch.no_grad():
         print("packed host", float(model.fused_elbo(pk.cpu(), None, seed=4)))
+    # host-buffer entry with chunks large enough for the host-compressed route (host thread pool packs a share
+    # of every chunk into pinned buffers while the rest crosses PCIe as is)
+    big_r, big_m = rows(3 * 8192 + 77, 200, 0.1, 11)
+    hm = vibo_b200.VIBO_2PL(1, 200, ability_merge="product").to(dev)
+    hm.host_chunk_person = 8192
+    with torch.no_grad():
+        print("host-compressed route", float(hm.fused_elbo(big_r.cpu().pin_memory(), big_m.cpu().pin_memory(), seed=4)),
+              "share", K._lib.load().vibo_host_pack_share(C.byref(K.make_desc(8192, 200, 1, 2, False)), 8192))
     # tcgen05 per-cell MLP (ragged tile edges)
     u, v = torch.randn(95, 64, device=dev), torch.randn(701, 64, device=dev)
     out = K.percell_mlp(u, v, None, None, torch.randn(64, 64, device=dev) * 0.2, torch.randn(64, device=dev),
