@@ -98,6 +98,22 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// The same wait for the roles that wait LONG (a whole tile): back off with nanosleep between polls.  A polling
+// warp issues three instructions per trip; sixteen link warps polling for the next tile took a quarter of the
+// SM's issue slots away from the packer / epilogue warps they were waiting for.
+__device__ __forceinline__ void bar_wait_idle(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(128);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -298,7 +314,7 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const int rows = (int)((p.P - row0 < kE5Rows) ? p.P - row0 : kE5Rows);
       uint8_t* s_flag = s_flags + b * kE5Rows;
       float* th_tile = s_theta + b * kE5Rows * kE5ThLd;
-      bar_wait(tile_done(b), aph ^ 1u);   // the link warps are done with this buffer (two tiles ago)
+      bar_wait_idle(tile_done(b), aph ^ 1u);   // the link warps are done with this buffer (two tiles ago)
       s_flag[e] = 0;
       asm volatile("bar.sync 2, 128;" ::: "memory");
       {
@@ -332,7 +348,7 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
       const bool exact = m < rows && s_flag[m] != 0;
-      bar_wait(acc_full(b), aph);
+      bar_wait_idle(acc_full(b), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[32];
       const uint32_t taddr = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)b * kE5N;
@@ -443,7 +459,7 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     uint32_t ph = 0, aph = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       uint32_t* bits = s_bits + b * kE5Rows * 32;
-      bar_wait(tile_done(b), aph ^ 1u);
+      bar_wait_idle(tile_done(b), aph ^ 1u);
       for (int kb = 0; kb < p.n_kb; ++kb) {
         bar_wait(full(s), ph);
         const uint32_t st = st_base + (uint32_t)s * kE5StageBytes + (uint32_t)pw * 32u * 128u;
@@ -454,14 +470,16 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         for (int rr = 0; rr < 32; ++rr) xs[rr] = lds32(st + (uint32_t)(rr >> 3) * 1024u + off8[rr & 7]);
         __syncwarp();
         if (lane == 0) bar_arrive(empty(s));   // this warp's reads of the stage are complete
-        uint32_t mine = 0;
-        if (!(p.debug & 2))
+        // one ballot per person row; lane 0 stores the word (a per-row "lane == row" select costs more
+        // instructions than the store it saves)
+        if (!(p.debug & 2)) {
+          uint32_t* dst = bits + kb * kE5Rows + pw * 32;
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          const uint32_t w = __ballot_sync(0xffffffffu, __uint_as_float(xs[rr]) > 0.5f);
-          mine = lane == rr ? w : mine;   // lane rr keeps the word of person 32 pw + rr
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t w = __ballot_sync(0xffffffffu, __uint_as_float(xs[rr]) > 0.5f);
+            if (lane == 0) dst[rr] = w;   // word of person 32 pw + rr
+          }
         }
-        bits[kb * kE5Rows + pw * 32 + lane] = mine;
         if (++s == kE5Stages) {
           s = 0;
           ph ^= 1u;
@@ -514,7 +532,7 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const uint32_t* bits = s_bits + b * kE5Rows * 32;
       const float* th_tile = s_theta + b * kE5Rows * kE5ThLd;
       const uint8_t* s_flag = s_flags + b * kE5Rows;
-      bar_wait(theta_full(b), tph);
+      bar_wait_idle(theta_full(b), tph);
       if (p.debug & 8) asm volatile("bar.sync 3, 768;" ::: "memory");
       f2_t ll2 = pack2(0.0f, 0.0f);
       // four persons per trip: one load of their flags and one of each item block's four bit words
