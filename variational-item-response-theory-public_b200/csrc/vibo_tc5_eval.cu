@@ -142,6 +142,27 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 // Log-likelihood of TWO cells (the warp's two item blocks for one person) in packed f32x2 arithmetic,
 // forward only; same clamp semantics as link_cell / cell_logistic_fast (vibo_stream_kernel.cuh): the
 // probability is clamped to [eps32, 1 - eps32] (utils.py:46-49 -> torch Bernoulli).  x0 / x1: the cell is 1.
+// 3PL: the probabilities of the two observed responses, clamped to [eps32, 1 - eps32] (the value the reference
+// takes the logarithm of).  The caller multiplies the probabilities of up to four persons before ONE lg2 per
+// item: four factors >= 1.19e-7 stay far above the smallest normal float.
+__device__ __forceinline__ f2_t prob_pair_3pl(f2_t z2, bool x0, bool x1, f2_t g2, f2_t omg2) {
+  float z0, z1;
+  unpack2(z2, z0, z1);
+  const f2_t zc2 = pack2(fmaxf(z0, -80.0f), fmaxf(z1, -80.0f));
+  float t0, t1;
+  unpack2(mul2(zc2, pack2(-kLog2e, -kLog2e)), t0, t1);
+  const f2_t e2 = pack2(ex2_approx(t0), ex2_approx(t1));
+  float w0, w1;
+  unpack2(add2(e2, pack2(1.0f, 1.0f)), w0, w1);
+  const f2_t r2 = pack2(rcp_approx(w0), rcp_approx(w1));
+  const f2_t pp2 = fma2(omg2, r2, g2);            // p = g + (1 - g) sigmoid(z)
+  const f2_t q2 = mul2(omg2, mul2(e2, r2));       // 1 - p = (1 - g) sigmoid(-z), full relative precision
+  float p0, p1, q0, q1;
+  unpack2(pp2, p0, p1);
+  unpack2(q2, q0, q1);
+  return pack2(fminf(fmaxf(x0 ? p0 : q0, kEps32), 1.0f - kEps32), fminf(fmaxf(x1 ? p1 : q1, kEps32), 1.0f - kEps32));
+}
+
 // Returns (ll0, ll1) in log2 units for the 3PL (caller scales by ln 2) / natural units for 1PL / 2PL.
 template <int MODEL>
 __device__ __forceinline__ f2_t eval_pair(f2_t z2, bool x0, bool x1, f2_t g2, f2_t omg2) {
@@ -536,12 +557,13 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       if (p.debug & 8) asm volatile("bar.sync 3, 768;" ::: "memory");
       f2_t ll2 = pack2(0.0f, 0.0f);
       // four persons per trip: one load of their flags and one of each item block's four bit words
-#pragma unroll 1
+#pragma unroll 2
       for (int p4 = 0; p4 < ((p.debug & 1) ? 0 : kE5Rows); p4 += 4) {
         const uint32_t f4 = *reinterpret_cast<const uint32_t*>(s_flag + p4);
         const uint4 w0 = *reinterpret_cast<const uint4*>(bits + kb0 * kE5Rows + p4);
         const uint4 w1 = *reinterpret_cast<const uint4*>(bits + kb1 * kE5Rows + p4);
         const uint32_t wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
+        f2_t prod2 = pack2(1.0f, 1.0f);   // 3PL: product of the four persons' probabilities per item
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if ((f4 >> (8 * q)) & 0xffu) continue;   // missing cells (handled by the epilogue) or past the end
@@ -557,7 +579,13 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             for (int d = 0; d < D; ++d) z2 = fma2(pack2(tv[d], tv[d]), na2[d], z2);
           }
           const bool x0 = (wa[q] & lane_bit) != 0, x1 = (wb[q] & lane_bit) != 0;
-          ll2 = fma2(eval_pair<MODEL>(z2, x0, x1, g2, omg2), scale2, ll2);
+          if (MODEL == 3) prod2 = mul2(prod2, prob_pair_3pl(z2, x0, x1, g2, omg2));
+          else ll2 = fma2(eval_pair<MODEL>(z2, x0, x1, g2, omg2), scale2, ll2);
+        }
+        if (MODEL == 3) {
+          float u0, u1;
+          unpack2(prod2, u0, u1);
+          ll2 = fma2(pack2(lg2_approx(u0), lg2_approx(u1)), scale2, ll2);
         }
       }
       float l0, l1;
