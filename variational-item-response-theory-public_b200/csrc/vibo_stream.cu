@@ -20,6 +20,11 @@ inline int gcd_i(int a, int b) {
 }
 
 // kind: 0 encode, 1 link, 2 encode backward.  n_parr: staged per-person arrays.
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v != nullptr ? atoi(v) : 0;
+}
+
 StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   StreamPlan pl;
   const int I = d.num_item, D = d.ability_dim;
@@ -49,6 +54,9 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   int ctas = 16 / NW;
   if (ctas < 1) ctas = 1;
   if (ctas > 8) ctas = 8;
+  // tuning overrides (experiments only): VIBO_STREAM_CTAS / _R / _NS replace the planned values
+  const int env_ctas = env_int("VIBO_STREAM_CTAS"), env_r = env_int("VIBO_STREAM_R"), env_ns = env_int("VIBO_STREAM_NS");
+  if (env_ctas > 0) ctas = env_ctas;
   const size_t budget = kStreamSmemCap / ctas - 1024;
   const int Qmax = 2 * D;
   int NS = 4, R = rq;
@@ -74,6 +82,8 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   while ((size_t)(R + rq) * row_bytes <= stage_cap && R + rq <= 64 && total(R + rq, 2, nullptr) <= budget) R += rq;
   // small problems: keep enough chunks to occupy the machine
   while (R > rq && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count() * ctas) R -= rq;
+  if (env_r > 0 && env_r % (rq < 8 ? rq : 4) == 0 && env_r % q_mask == 0 && env_r % q_parr == 0) R = env_r;
+  if (env_ns > 0 && env_ns <= kStreamMaxStages) NS = env_ns;
   while (NS > 2 && total(R, NS, nullptr) > budget) --NS;
   if (total(R, NS, nullptr) > kStreamSmemCap) return pl;
   pl.smem = total(R, NS, &pl);

@@ -415,6 +415,53 @@ __device__ __forceinline__ void link_cell(float z, float x, float g, float omg, 
   }
 }
 
+// Two 3PL cells (one lane's item pair) in packed f32x2 arithmetic, with TWO MUFU operations per cell instead of
+// four.  With E = exp(-zc), w = 1 + E, v = 1 + g E:  p = g + (1-g)/(1+E) = v / w, so ONE reciprocal
+// R = 1 / (w v) yields both sigmoid(z) = R v and 1 / v = R w (so sigmoid(-z) / p = E / v); for x = 0 the factor
+// d ll/d u * sigmoid(-z) = -sigmoid(-z) / ((1-g) sigmoid(-z)) is the per-item constant -1/(1-g) (nio2).
+// zc = max(z, -40) keeps w v finite; below -40 sigmoid(z) < 4.3e-18 moves p = g + (1-g) sigmoid(z) by less
+// than 4e-11 of the eps32 floor the clamp holds it above, so value and gradient are unchanged.
+// Returns the clamped probabilities of the observed responses (u2: the caller multiplies them over four
+// persons before one lg2), and with GRAD t02 = d ll/d u * sigmoid(-z) (zero outside the clamp) and
+// dz2 = t0 sigmoid(z) (1-g), as link_cell (no validity weight: the caller zeroes a for padding lanes).
+template <bool GRAD>
+__device__ __forceinline__ void link_pair_3pl(f2_t z2, float x0, float x1, f2_t g2, f2_t omg2, f2_t nio2, f2_t& u2,
+                                              f2_t& dz2, f2_t& t02) {
+  float z0, z1;
+  unpack2(z2, z0, z1);
+  const f2_t one2 = pack2(1.0f, 1.0f);
+  float s0, s1;
+  unpack2(mul2(pack2(fmaxf(z0, -40.0f), fmaxf(z1, -40.0f)), pack2(-kLog2e, -kLog2e)), s0, s1);
+  const f2_t e2 = pack2(ex2_approx(s0), ex2_approx(s1));
+  const f2_t w2 = add2(e2, one2), v2 = fma2(g2, e2, one2);
+  float wv0, wv1;
+  unpack2(mul2(w2, v2), wv0, wv1);
+  const f2_t R2 = pack2(rcp_approx(wv0), rcp_approx(wv1));
+  const f2_t r2 = mul2(R2, v2);       // sigmoid(z)
+  const f2_t sn2 = mul2(e2, r2);      // sigmoid(-z)
+  float p0, p1, q0, q1;
+  unpack2(fma2(omg2, r2, g2), p0, p1);
+  unpack2(mul2(omg2, sn2), q0, q1);   // 1 - p with full relative precision
+  const bool b0 = x0 > 0.5f, b1 = x1 > 0.5f;
+  const float u0 = b0 ? p0 : q0, u1 = b1 ? p1 : q1;
+  const float c0 = fminf(fmaxf(u0, kEps32), 1.0f - kEps32), c1 = fminf(fmaxf(u1, kEps32), 1.0f - kEps32);
+  u2 = pack2(c0, c1);
+  if (GRAD) {
+    float t0, t1, n0, n1;
+    unpack2(mul2(e2, mul2(w2, R2)), t0, t1);   // x = 1: sigmoid(-z) / p = (E / w) / (v / w) = E / v = E w R
+    unpack2(nio2, n0, n1);
+    t0 = b0 ? t0 : n0;
+    t1 = b1 ? t1 : n1;
+    t0 = (c0 == u0) ? t0 : 0.0f;
+    t1 = (c1 == u1) ? t1 : 0.0f;
+    t02 = pack2(t0, t1);
+    dz2 = mul2(mul2(t02, r2), omg2);
+  } else {
+    t02 = pack2(0.0f, 0.0f);
+    dz2 = t02;
+  }
+}
+
 template <int MODEL, int D, int M, int NR, bool GRAD>
 __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant__ StreamParams p,
                                                           const float* __restrict__ item_feat,
@@ -435,6 +482,7 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
   bool valid[2 * MP];
   f2_t a2[MP][DA], b2[MP], acc2[MP][GRAD ? F : 1];   // pairs over the lane's items (2k, 2k+1)
   float gs[2 * MP], omg[2 * MP], wv[2 * MP];
+  f2_t g2k[MP], omg2k[MP], nio2k[MP], wl2k[MP];   // 3PL only
 #pragma unroll
   for (int k = 0; k < MP; ++k) {
     float av[2][DA], bv[2];
@@ -449,8 +497,10 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
         av[h][0] = 0.0f;
         gs[m] = 0.0f;
       } else {
+        // 3PL: a padding lane carries a = 0, so its d ll/d z drops out of the per-person sums without a weight
 #pragma unroll
-        for (int d = 0; d < D; ++d) av[h][d] = item_feat[(size_t)joff[m] * F + d];
+        for (int d = 0; d < D; ++d)
+          av[h][d] = (MODEL == 3 && !valid[m]) ? 0.0f : item_feat[(size_t)joff[m] * F + d];
         bv[h] = item_feat[(size_t)joff[m] * F + D];
         gs[m] = MODEL == 3 ? 1.0f / (1.0f + expf(-item_feat[(size_t)joff[m] * F + D + 1])) : 0.0f;
       }
@@ -459,9 +509,15 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
     }
     b2[k] = pack2(bv[0], bv[1]);
 #pragma unroll
-    for (int d = 0; d < DA; ++d) a2[k][d] = pack2(av[0][d], av[1][d]);
+    for (int d = 0; d < DA; ++d) a2[k][d] = pack2(-av[0][d], -av[1][d]);   // the NEGATED discriminations
 #pragma unroll
     for (int f = 0; f < (GRAD ? F : 1); ++f) acc2[k][f] = pack2(0.0f, 0.0f);
+    if (MODEL == 3) {   // per-pair constants of link_pair_3pl
+      g2k[k] = pack2(gs[2 * k], gs[2 * k + 1]);
+      omg2k[k] = pack2(omg[2 * k], omg[2 * k + 1]);
+      nio2k[k] = pack2(-1.0f / omg[2 * k], -1.0f / omg[2 * k + 1]);
+      wl2k[k] = pack2(wv[2 * k] * kLn2f, wv[2 * k + 1] * kLn2f);
+    }
   }
   float ll_lane = 0.0f;   // flushed into a double once per stage
   double ll_acc = 0.0;
@@ -515,66 +571,103 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
       const float* xr = sx + r0 * I;
       const uint8_t* mr = sm + r0 * I;
       const float* tr = sth + r0 * D;
+      // 3PL: product of the clamped probabilities of up to four rows per item, ONE lg2 per item and four rows
+      // (four factors >= eps32 stay far above the smallest normal float)
+      f2_t prod2[MP];
+#pragma unroll
+      for (int k = 0; k < MP; ++k) prod2[k] = pack2(1.0f, 1.0f);
 #pragma unroll
       for (int rr = 0; rr < NR; ++rr, xr += I, mr += I, tr += D) {
-        float gth[D];
+        f2_t gth2[D];   // the lane's two halves of d LL / d theta; added at the end of the row
 #pragma unroll
-        for (int d = 0; d < D; ++d) gth[d] = 0.0f;
+        for (int d = 0; d < D; ++d) gth2[d] = pack2(0.0f, 0.0f);
         if (!RAGGED || r0 + rr < rows) {
-          float th[D], tsum = 0.0f;
+          f2_t th2[D];
+          float tsum = 0.0f;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            th[d] = tr[d];
-            tsum += th[d];
+            const float thd = tr[d];
+            th2[d] = pack2(thd, thd);
+            tsum += thd;
           }
 #pragma unroll
           for (int k = 0; k < MP; ++k) {
-            float x[2], ll[2], dz[2], t0[2];
             f2_t z2 = b2[k];
             if (MODEL == 1) {
               z2 = add2(z2, pack2(tsum, tsum));
             } else {
 #pragma unroll
-              for (int d = 0; d < D; ++d) z2 = fma2(pack2(-th[d], -th[d]), a2[k][d], z2);
+              for (int d = 0; d < D; ++d) z2 = fma2(th2[d], a2[k][d], z2);   // z = b - theta . a
             }
-            float z[2];
-            unpack2(z2, z[0], z[1]);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int m = 2 * k + h;
-              x[h] = xr[joff[m]];
-              link_cell<MODEL>(z[h], x[h], gs[m], omg[m], wv[m], ll[h], dz[h], t0[h]);
+            f2_t dz2, t02;
+            if (MODEL == 3) {
+              f2_t u2;
+              link_pair_3pl<GRAD>(z2, xr[joff[2 * k]], xr[joff[2 * k + 1]], g2k[k], omg2k[k], nio2k[k], u2, dz2,
+                                  t02);
               if (OMASK) {
-                const bool o = mr[joff[m]] != 0;
-                ll[h] = o ? ll[h] : 0.0f;
-                dz[h] = o ? dz[h] : 0.0f;
-                t0[h] = o ? t0[h] : 0.0f;
+                const bool o0 = mr[joff[2 * k]] != 0, o1 = mr[joff[2 * k + 1]] != 0;
+                float a0, a1, d0, d1, e0, e1;
+                unpack2(u2, a0, a1);
+                u2 = pack2(o0 ? a0 : 1.0f, o1 ? a1 : 1.0f);
+                if (GRAD) {
+                  unpack2(dz2, d0, d1);
+                  unpack2(t02, e0, e1);
+                  dz2 = pack2(o0 ? d0 : 0.0f, o1 ? d1 : 0.0f);
+                  t02 = pack2(o0 ? e0 : 0.0f, o1 ? e1 : 0.0f);
+                }
               }
-              ll_lane = fmaf(wv[m], ll[h], ll_lane);
+              prod2[k] = mul2(prod2[k], u2);
+            } else {
+              float z[2], dz[2];
+              unpack2(z2, z[0], z[1]);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int m = 2 * k + h;
+                float ll1, t0u;
+                link_cell<MODEL>(z[h], xr[joff[m]], gs[m], omg[m], wv[m], ll1, dz[h], t0u);
+                if (OMASK) {
+                  const bool o = mr[joff[m]] != 0;
+                  ll1 = o ? ll1 : 0.0f;
+                  dz[h] = o ? dz[h] : 0.0f;
+                }
+                ll_lane = fmaf(wv[m], ll1, ll_lane);
+              }
+              dz2 = pack2(dz[0], dz[1]);
+              t02 = pack2(0.0f, 0.0f);
             }
             if (GRAD) {
-              const f2_t dz2 = pack2(dz[0], dz[1]);
               if (MODEL == 1) {
-                gth[0] += dz[0] + dz[1];
+                gth2[0] = add2(gth2[0], dz2);
                 acc2[k][0] = add2(acc2[k][0], dz2);
               } else {
-                const f2_t ndz2 = pack2(-dz[0], -dz[1]);
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                  float lo, hi;
-                  unpack2(a2[k][d], lo, hi);
-                  gth[d] = fmaf(-dz[0], lo, fmaf(-dz[1], hi, gth[d]));
-                  acc2[k][d] = fma2(ndz2, pack2(th[d], th[d]), acc2[k][d]);
+                  gth2[d] = fma2(dz2, a2[k][d], gth2[d]);        // d LL/d theta = -sum dz a
+                  acc2[k][d] = fma2(dz2, th2[d], acc2[k][d]);    // +sum dz theta: negated when it is stored
                 }
                 acc2[k][D] = add2(acc2[k][D], dz2);
-                if (MODEL == 3) acc2[k][D + 1] = add2(acc2[k][D + 1], pack2(t0[0], t0[1]));
+                if (MODEL == 3) acc2[k][D + 1] = add2(acc2[k][D + 1], t02);
               }
             }
           }
         }
+        if (MODEL == 3 && ((rr & 3) == 3 || rr == NR - 1)) {
+#pragma unroll
+          for (int k = 0; k < MP; ++k) {
+            float u0, u1, w0, w1;
+            unpack2(prod2[k], u0, u1);
+            unpack2(wl2k[k], w0, w1);
+            ll_lane = fmaf(w0, lg2_approx(u0), fmaf(w1, lg2_approx(u1), ll_lane));
+            prod2[k] = pack2(1.0f, 1.0f);
+          }
+        }
         if (GRAD) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) part[d][rr] = MODEL == 1 ? gth[0] : gth[d];
+          for (int d = 0; d < D; ++d) {
+            float lo, hi;
+            unpack2(gth2[MODEL == 1 ? 0 : d], lo, hi);
+            part[d][rr] = lo + hi;
+          }
         }
       }
       if (GRAD) {
@@ -647,8 +740,8 @@ __global__ void __launch_bounds__(512) link_stream_kernel(const __grid_constant_
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int m = 2 * k + h;
-          // 3PL guess logit: d ll/d gamma = g (1 - g) sum t0
-          const float sc = (MODEL == 3 && f == D + 1) ? gs[m] * omg[m] : 1.0f;
+          // d ll/d a = -sum dz theta (the registers hold +sum); 3PL guess logit: d ll/d gamma = g (1 - g) sum t0
+          const float sc = (MODEL == 3 && f == D + 1) ? gs[m] * omg[m] : ((MODEL != 1 && f < D) ? -1.0f : 1.0f);
           if (valid[m]) dst[(size_t)joff[m] * F + f] = v[h] * sc;
         }
       }

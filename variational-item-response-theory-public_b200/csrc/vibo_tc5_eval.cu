@@ -42,6 +42,7 @@ struct E5Params {
   int64_t P;
   int I, n_kb, missing_policy, form;
   int debug;   // VIBO_E5_DEBUG (tool runs only): 1 skip the link arithmetic, 2 skip the bit packing, 4 skip the mask scan;
+               // 16: packers hand a stage back after the ballots; 128: no hardening of the hand-offs (A/B runs);
                // 8: two 768-thread barriers per tile put the epilogue / packer warps and the link warps in lock-step --
                // racecheck does not credit an mbarrier arrive / wait pair as ordering ordinary shared-memory accesses
   int64_t person_offset;
@@ -459,6 +460,7 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       } else {
         s_flag[m] = 1;   // rows past the end of the matrix: the link warps skip them
       }
+      if (!(p.debug & 128)) __threadfence_block();   // theta / flags are performed before the arrive below
       __syncwarp();
       if (lane == 0) bar_arrive(theta_full(b));   // release: theta, flags of this tile
       if (p.debug & 8) {   // lock-step with the link warps (racecheck runs, see E5Params::debug)
@@ -489,23 +491,36 @@ tc5_eval_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         uint32_t xs[32];
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr) xs[rr] = lds32(st + (uint32_t)(rr >> 3) * 1024u + off8[rr & 7]);
-        __syncwarp();
-        if (lane == 0) bar_arrive(empty(s));   // this warp's reads of the stage are complete
+        // The ballot of the LAST row loaded is taken first: warps issue in order, so once it has issued every
+        // load of this stage has returned its data and the stage can be handed back (an arrive placed right
+        // behind the loads would rely on the load and mbarrier pipes staying in order).
+        uint32_t w_last = 0;
+        if (!(p.debug & 128)) w_last = __ballot_sync(0xffffffffu, __uint_as_float(xs[31]) > 0.5f);
+        if (!(p.debug & 16)) {
+          __syncwarp();
+          if (lane == 0) bar_arrive(empty(s));   // this warp's reads of the stage are complete
+        }
         // one ballot per person row; lane 0 stores the word (a per-row "lane == row" select costs more
         // instructions than the store it saves)
         if (!(p.debug & 2)) {
           uint32_t* dst = bits + kb * kE5Rows + pw * 32;
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
-            const uint32_t w = __ballot_sync(0xffffffffu, __uint_as_float(xs[rr]) > 0.5f);
+            uint32_t w = w_last;
+            if (rr < 31 || (p.debug & 128)) w = __ballot_sync(0xffffffffu, __uint_as_float(xs[rr]) > 0.5f);
             if (lane == 0) dst[rr] = w;   // word of person 32 pw + rr
           }
+        }
+        if (p.debug & 16) {   // hand the stage back only after the ballots consumed every loaded word
+          __syncwarp();
+          if (lane == 0) bar_arrive(empty(s));
         }
         if (++s == kE5Stages) {
           s = 0;
           ph ^= 1u;
         }
       }
+      if (!(p.debug & 128)) __threadfence_block();   // the ballot words are performed before the arrive below
       __syncwarp();
       if (lane == 0) bar_arrive(theta_full(b));   // release: the bits of this tile
       if (p.debug & 8) {   // lock-step with the link warps (racecheck runs, see E5Params::debug)
