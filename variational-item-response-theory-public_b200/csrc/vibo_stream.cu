@@ -56,6 +56,11 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   if (ctas > 8) ctas = 8;
   // tuning overrides (experiments only): VIBO_STREAM_CTAS / _R / _NS replace the planned values
   const int env_ctas = env_int("VIBO_STREAM_CTAS"), env_r = env_int("VIBO_STREAM_R"), env_ns = env_int("VIBO_STREAM_NS");
+  // narrow rows (at most three slab warps per CTA): the per-chunk latency chain (copy -> wait -> reduce ->
+  // barrier) dominates, so run as many small CTAs as fit (measured on 428478 x 95: encode 127 -> 92 us,
+  // encode backward 116 -> 97 us, link 140 -> 134 us against five CTAs with 23 KB stages)
+  const bool narrow = NW <= 3;
+  if (narrow) ctas = 8;
   if (env_ctas > 0) ctas = env_ctas;
   const size_t budget = kStreamSmemCap / ctas - 1024;
   const int Qmax = 2 * D;
@@ -78,7 +83,7 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   };
   // grow R while a stage stays <= 24 KB and R <= 64, then fit NS
   // long rows (one CTA per SM): 16-row stages halve the number of CTA-wide barriers per row
-  const size_t stage_cap = (ctas == 1 ? 84 : 24) * 1024;
+  const size_t stage_cap = (ctas == 1 ? 84 : (narrow ? 8 : 24)) * 1024;
   while ((size_t)(R + rq) * row_bytes <= stage_cap && R + rq <= 64 && total(R + rq, 2, nullptr) <= budget) R += rq;
   // small problems: keep enough chunks to occupy the machine
   while (R > rq && (d.num_person + R - 1) / R < 2 * (int64_t)sm_count() * ctas) R -= rq;
