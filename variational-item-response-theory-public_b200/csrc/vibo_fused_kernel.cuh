@@ -181,6 +181,9 @@ __device__ __forceinline__ void fused_issue_chunk(const FusedParams& p, const Fu
     const float* ge = p.eps + row0 * D;
     float* se = reinterpret_cast<float*>(st + L.eps_off);
     for (int k = lane; k < rows * D; k += 32) se[k] = ge[k];
+    // the hand-copied cells are performed before the arrive that publishes them (an mbarrier arrive is not
+    // ordered behind the warp's own in-flight shared-memory accesses on B200)
+    __threadfence_block();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
   }
