@@ -57,10 +57,11 @@ StreamPlan stream_plan(const vibo_desc& d, int kind, int n_parr) {
   // tuning overrides (experiments only): VIBO_STREAM_CTAS / _R / _NS replace the planned values
   const int env_ctas = env_int("VIBO_STREAM_CTAS"), env_r = env_int("VIBO_STREAM_R"), env_ns = env_int("VIBO_STREAM_NS");
   // narrow rows (at most three slab warps per CTA): the per-chunk latency chain (copy -> wait -> reduce ->
-  // barrier) dominates, so run as many small CTAs as fit (measured on 428478 x 95: encode 127 -> 92 us,
-  // encode backward 116 -> 97 us, link 140 -> 134 us against five CTAs with 23 KB stages)
+  // barrier) dominates, so run many small CTAs with two ~8 KB stages each (measured on 428478 x 95 against
+  // five CTAs with 23 KB stages: encode 127 -> 90 us, encode backward 116 -> 97 us, link with gradients
+  // 140 -> 124 us, link 107 -> 89 us; 8 / 12 / 14 / 16 CTAs were all slower than 10)
   const bool narrow = NW <= 3;
-  if (narrow) ctas = 8;
+  if (narrow) ctas = 10;
   if (env_ctas > 0) ctas = env_ctas;
   const size_t budget = kStreamSmemCap / ctas - 1024;
   const int Qmax = 2 * D;
