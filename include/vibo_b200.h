@@ -195,6 +195,22 @@ int vibo_encode_backward(const vibo_desc* desc, const float* response, const uin
                          size_t workspace_bytes, void* stream);
 
 /*
+ * The same pair for the UNCONDITIONAL posterior with one pass over the rows instead of two: the
+ * unconditional table has one expert per response value (models.py:575-582 evaluated on r in {0, 1}), so
+ * the posterior and its backward depend on a row only through counts (P, 2) = (observed ones, observed
+ * cells).  vibo_encode_counts writes them next to the posterior; vibo_encode_backward_counts forms
+ * d loss / d table (2, 1, 2D) from them without reading response / mask again.
+ * VIBO_ERR_UNSUPPORTED for a conditional posterior or rows that are not 16-byte aligned.
+ */
+int vibo_encode_counts(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                       const float* table, float* ability_mu, float* ability_logvar,
+                       float* precision_sum, float* counts, void* stream);
+int vibo_encode_backward_counts(const vibo_desc* desc, const float* counts, const float* table,
+                                const float* ability_mu, const float* precision_sum,
+                                const float* g_ability_mu, const float* g_ability_logvar, float* g_table,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * link + log-likelihood without materialising response_mu:
  *   LL = sum_ij o_ij log Bernoulli(x_ij ; irt_model(ability, item_feat))
  * (models.py:729-766 + utils.py:46-49 + the .sum() of models.py:399).

@@ -229,6 +229,26 @@ def encode_backward(response, mask, table, ability_dim, S, ability_mu, g_mu, g_l
     return g_table
 
 
+def encode_backward_counts(counts, table, ability_dim, S, ability_mu, g_mu, g_logvar):
+    """encode_backward for the UNCONDITIONAL table (one expert per response value, It = 1) from the
+    per-person counts (observed ones, observed cells) of person_counts: the row enters A^r, B^r only as
+    n^r_i = #{j: o_ij = 1, x_ij = r}, so A^r = sum_i n^r_i GN_i.  Spec of vibo_encode_backward_counts;
+    equal to encode_backward on the same inputs (tests/test_oracle_golden.py)."""
+    D = ability_dim
+    assert table.shape[1] == 1
+    mu, lam, tau = expert_precision(table, D)
+    GN = g_mu / S
+    GS = -(g_mu * ability_mu + g_logvar) / S
+    n1 = counts[:, 0:1].astype(table.dtype)
+    n0 = counts[:, 1:2].astype(table.dtype) - n1
+    A = np.stack([(n0 * GN).sum(0), (n1 * GN).sum(0)])[:, None, :]   # (2, 1, D)
+    B = np.stack([(n0 * GS).sum(0), (n1 * GS).sum(0)])[:, None, :]
+    g_table = np.empty_like(table)
+    g_table[..., :D] = tau * A
+    g_table[..., D:] = (mu * A + B) * (-np.exp(lam) * tau ** 2)
+    return g_table
+
+
 ELBO_KL = 0      # use_kl_divergence=True, models.py:427-430
 ELBO_SAMPLE = 1  # use_kl_divergence=False, models.py:432-441
 

@@ -96,6 +96,20 @@ def encode_backward(response, mask, table, ability_mu, precision_sum, g_mu, g_lo
     return _t(g, response)
 
 
+def encode_counts(response, mask, table, *, missing_policy=0):
+    mu, lv, S = encode(response, mask, table, conditional=False, missing_policy=missing_policy)
+    n0, n1, _ = KS.person_counts(_np(response), _np(mask, np.uint8))
+    return mu, lv, S, _t(np.stack([n1, n0 + n1], 1), response)   # (observed ones, observed cells)
+
+
+def encode_backward_counts(counts, table, ability_mu, precision_sum, g_mu, g_logvar, *, num_item,
+                           missing_policy=0):
+    D = table.shape[-1] // 2
+    g = KS.encode_backward_counts(_np(counts), _np(table), D, _np(precision_sum), _np(ability_mu), _np(g_mu),
+                                  _np(g_logvar))
+    return _t(g, table)
+
+
 def link_loglik(response, mask, ability, item_feat, *, irt_model, want_grads=True):
     r = KS.link_loglik(_np(response), _np(mask, np.uint8), _np(ability), _np(item_feat), irt_model,
                        want_grads)
@@ -123,6 +137,7 @@ def _check_rows(response, mask):
 def install(monkeypatch):
     import vibo_b200
     K = vibo_b200.kernels
-    for name in ("fused_elbo", "encode", "encode_backward", "link_loglik", "decode",
+    for name in ("fused_elbo", "encode", "encode_backward", "encode_counts", "encode_backward_counts",
+                 "link_loglik", "decode",
                  "bernoulli_loglik", "_check_rows", "philox_normal"):
         monkeypatch.setattr(K, name, globals()[name])

@@ -185,3 +185,21 @@ def test_mean_merge_spec_matches_reference(name):
     mu, lv = torch.chunk(o, 2, dim=1)
     assert max_rel(mu.numpy(), rec["ability_mu"]) < 1e-5
     assert max_rel(lv.numpy(), rec["ability_logvar"]) < 1e-5
+
+
+@pytest.mark.parametrize("D,policy,missing", [(1, 0, 0.0), (1, 0, 0.1), (2, 1, 0.3), (5, 0, 0.2)])
+def test_count_based_unconditional_encode_backward_spec(D, policy, missing):
+    """oracle.kernel_spec.encode_backward_counts (the spec of vibo_encode_backward_counts: table gradient of the
+    unconditional posterior from per-person counts) equals the row-level encode_backward it replaces."""
+    rng = np.random.default_rng(11 + D)
+    P, I = 257, 95
+    resp = (rng.random((P, I)) < 0.55).astype(np.float64)
+    mask = (rng.random((P, I)) >= missing).astype(np.uint8)
+    resp[mask == 0] = -1.0
+    table = 0.4 * rng.normal(size=(2, 1, 2 * D))
+    enc = KS.encode(resp, mask, table, D, policy)
+    g_mu, g_lv = rng.normal(size=(P, D)), rng.normal(size=(P, D))
+    ref = KS.encode_backward(resp, mask, table, D, enc["S"], enc["ability_mu"], g_mu, g_lv)
+    n0, n1, _ = KS.person_counts(resp, mask)
+    got = KS.encode_backward_counts(np.stack([n1, n0 + n1], 1), table, D, enc["S"], enc["ability_mu"], g_mu, g_lv)
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)

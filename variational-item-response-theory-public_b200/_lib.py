@@ -53,6 +53,8 @@ SIGNATURES = {
     "vibo_unpack": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_encode": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p]),
     "vibo_person_counts": (C.c_int, [_PD, _p, _p, _p, _p]),
+    "vibo_encode_counts": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "vibo_encode_backward_counts": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_encode_backward": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_link_loglik": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "vibo_decode": (C.c_int, [_PD, _p, _p, _p, _p]),

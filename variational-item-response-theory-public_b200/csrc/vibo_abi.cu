@@ -78,6 +78,7 @@ size_t general_workspace_bytes(const vibo_desc* d) {
   b += (align_up(4 * P * D, 256) + 256) * 8;                // per-person float scratch
   b += align_up(4 * G * I * F, 256) + 256;                  // item-gradient partials
   b += align_up(4 * G * 2 * I * 2 * D, 256) + 256;          // expert-table partials
+  b += align_up(4 * P * 2, 256) + 256;                      // per-person counts (unconditional backward)
   return b + 4096;
 }
 
@@ -182,9 +183,19 @@ static int fused_elbo_impl(const vibo_desc* desc, const float* response, const u
   float* g_lv = ws.take<float>(PD);
   float* part_g = ws.take<float>(G * d.num_item * F);
   float* part_ab = ws.take<float>(G * 2 * d.num_item * 2 * d.ability_dim);
+  float* counts = ws.take<float>((size_t)d.num_person * 2);
   if (!ws.ok()) return fail(VIBO_ERR_WORKSPACE, "workspace carve overflow");
 
-  VIBO_CUDA(vibo::launch_encode(d, response, mask, table, amu, alv, S, st), "encode");
+  // unconditional posterior with gradients: the encode pass also leaves the per-person counts, from which the
+  // backward forms the table gradient without a third pass over the rows
+  bool have_counts = false;
+  if (grad && !d.conditional) {
+    const cudaError_t ec = vibo::launch_encode_counts(d, response, mask, table, amu, alv, S, counts, st);
+    if (ec == cudaSuccess) have_counts = true;
+    else if (ec != cudaErrorNotSupported) return cuda_fail(ec, "encode");
+    else (void)cudaGetLastError();
+  }
+  if (!have_counts) VIBO_CUDA(vibo::launch_encode(d, response, mask, table, amu, alv, S, st), "encode");
   VIBO_CUDA(vibo::launch_person_forward(d, amu, alv, eps_ability, seed, seed_dev,
                                         eps_ability ? nullptr : eps_buf, th, part_term,
                                         out_scalars + 1, st),
@@ -197,8 +208,13 @@ static int fused_elbo_impl(const vibo_desc* desc, const float* response, const u
     VIBO_CUDA(vibo::launch_person_backward(d, beta, amu, alv, eps_ability ? eps_ability : eps_buf, th,
                                            g_ab, g_mu, g_lv, st),
               "person_backward");
-    VIBO_CUDA(vibo::launch_encode_bwd(d, response, mask, table, amu, S, g_mu, g_lv, g_table, part_ab, st),
-              "encode_backward");
+    if (have_counts) {
+      VIBO_CUDA(vibo::launch_encode_bwd_counts(d, counts, table, amu, S, g_mu, g_lv, g_table, part_ab, st),
+                "encode_backward (counts)");
+    } else {
+      VIBO_CUDA(vibo::launch_encode_bwd(d, response, mask, table, amu, S, g_mu, g_lv, g_table, part_ab, st),
+                "encode_backward");
+    }
   }
   return VIBO_OK;
 }
@@ -246,6 +262,49 @@ int vibo_encode(const vibo_desc* desc, const float* response, const uint8_t* mas
   VIBO_CUDA(vibo::launch_encode(*desc, response, mask, table, ability_mu, ability_logvar,
                                 precision_sum, static_cast<cudaStream_t>(stream)),
             "encode");
+  return VIBO_OK;
+}
+
+int vibo_encode_counts(const vibo_desc* desc, const float* response, const uint8_t* mask,
+                       const float* table, float* ability_mu, float* ability_logvar,
+                       float* precision_sum, float* counts, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!response || !mask || !table || !ability_mu || !ability_logvar || !precision_sum || !counts)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (desc->conditional) return fail(VIBO_ERR_UNSUPPORTED, "vibo_encode_counts: unconditional posterior only");
+  if (int rc = check_items(desc)) return rc;
+  if (desc->num_person == 0) return VIBO_OK;
+  const cudaError_t e = vibo::launch_encode_counts(*desc, response, mask, table, ability_mu, ability_logvar,
+                                                   precision_sum, counts, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorNotSupported) {
+    (void)cudaGetLastError();
+    return fail(VIBO_ERR_UNSUPPORTED, "vibo_encode_counts: rows not 16-byte aligned (use vibo_encode)");
+  }
+  VIBO_CUDA(e, "encode_counts");
+  return VIBO_OK;
+}
+
+int vibo_encode_backward_counts(const vibo_desc* desc, const float* counts, const float* table,
+                                const float* ability_mu, const float* precision_sum,
+                                const float* g_ability_mu, const float* g_ability_logvar, float* g_table,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_desc(desc)) return rc;
+  if (!counts || !table || !ability_mu || !precision_sum || !g_ability_mu || !g_ability_logvar || !g_table)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  if (desc->conditional)
+    return fail(VIBO_ERR_UNSUPPORTED, "vibo_encode_backward_counts: unconditional posterior only");
+  if (workspace == nullptr || workspace_bytes < vibo_workspace_bytes(desc))
+    return fail(VIBO_ERR_WORKSPACE, "workspace smaller than vibo_workspace_bytes(desc)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (desc->num_person == 0) {
+    VIBO_CUDA(cudaMemsetAsync(g_table, 0, sizeof(float) * 2 * 2 * desc->ability_dim, st), "memset");
+    return VIBO_OK;
+  }
+  Carve ws(workspace, workspace_bytes);
+  float* part = ws.take<float>((size_t)vibo::sm_count() * 4 * 4 * desc->ability_dim);
+  VIBO_CUDA(vibo::launch_encode_bwd_counts(*desc, counts, table, ability_mu, precision_sum, g_ability_mu,
+                                           g_ability_logvar, g_table, part, st),
+            "encode_backward_counts");
   return VIBO_OK;
 }
 

@@ -13,6 +13,8 @@
 // combined across the NS slabs through shared memory in a fixed order
 // (deterministic).  CTAs are persistent over row tiles; per-CTA partials go to
 // the workspace and a small second kernel reduces them in a fixed order.
+#include <cstdlib>
+
 #include "vibo_common.cuh"
 #include "vibo_kernels.h"
 
@@ -232,6 +234,49 @@ __global__ void __launch_bounds__(32 * kSumSlices) encode_bwd_finalize_kernel(in
     const float tau = 1.0f / (el + kPoeEps);
     g_table[((size_t)r * It + jt) * 2 * D + d] = tau * (float)ta;
     g_table[((size_t)r * It + jt) * 2 * D + D + d] = (mu * (float)ta + (float)tb) * (-el * tau * tau);
+  }
+}
+
+// Unconditional encode backward from the forward pass's per-person counts.  The unconditional table has ONE
+// entry per response value, so A^r = sum_i n^r_i GN_i and B^r = sum_i n^r_i GS_i (n^1 = observed ones,
+// n^0 = observed - ones; missing cells carry no table entry under either policy) need 16 + 16 D bytes per
+// person instead of a second pass over the 5 I bytes of its row.  part: [grid][2][1][2D], the layout
+// encode_bwd_finalize_kernel reads for the unconditional table.  Fixed summation order.
+template <int D>
+__global__ void __launch_bounds__(256) encode_bwd_counts_kernel(int64_t P, const float* __restrict__ counts,
+                                                                const float* __restrict__ amu,
+                                                                const float* __restrict__ S,
+                                                                const float* __restrict__ g_mu,
+                                                                const float* __restrict__ g_lv,
+                                                                float* __restrict__ part) {
+  float acc[4 * D];   // [r][A | B][d]
+#pragma unroll
+  for (int q = 0; q < 4 * D; ++q) acc[q] = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 c = reinterpret_cast<const float2*>(counts)[i];
+    const float n1 = c.x, n0 = c.y - c.x;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float sv = S[i * D + d], gm = g_mu[i * D + d];
+      const float gn = gm / sv, gs = -(gm * amu[i * D + d] + g_lv[i * D + d]) / sv;
+      acc[d] = fmaf(n0, gn, acc[d]);
+      acc[D + d] = fmaf(n0, gs, acc[D + d]);
+      acc[2 * D + d] = fmaf(n1, gn, acc[2 * D + d]);
+      acc[3 * D + d] = fmaf(n1, gs, acc[3 * D + d]);
+    }
+  }
+  __shared__ float s_w[8][4 * D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 4 * D; ++q) {
+    const float v = warp_sum(acc[q]);
+    if (lane == 0) s_w[warp][q] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < 4 * D) {
+    float v = 0.0f;
+    for (int w = 0; w < 8; ++w) v += s_w[w][threadIdx.x];
+    part[(size_t)blockIdx.x * 4 * D + threadIdx.x] = v;
   }
 }
 
@@ -609,6 +654,36 @@ cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8
   VIBO_SWITCH_D(d.ability_dim,
                 e = launch_encode_bwd_d<kD>(d, resp, mask, table, amu, S, g_mu, g_lv, g_table, part, st));
   return e;
+}
+
+cudaError_t launch_encode_counts(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                 const float* table, float* mu, float* lv, float* S, float* counts,
+                                 cudaStream_t st) {
+  const char* off = getenv("VIBO_DISABLE_COUNTS_BWD");
+  if (off != nullptr && off[0] == '1') return cudaErrorNotSupported;
+  const cudaError_t e = stream_encode_counts(d, resp, mask, table, mu, lv, S, counts, st);
+  if (e == cudaSuccess) note_launch();
+  return e;
+}
+
+cudaError_t launch_encode_bwd_counts(const vibo_desc& d, const float* counts, const float* table,
+                                     const float* amu, const float* S, const float* g_mu, const float* g_lv,
+                                     float* g_table, float* part, cudaStream_t st) {
+  if (d.conditional) return cudaErrorNotSupported;
+  int64_t blocks = (d.num_person + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const int grid = (int)blocks;
+  cudaError_t e = cudaSuccess;
+  VIBO_SWITCH_D(d.ability_dim,
+                (encode_bwd_counts_kernel<kD><<<grid, 256, 0, st>>>(d.num_person, counts, amu, S, g_mu, g_lv, part)));
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int n = 2 * d.ability_dim;
+  encode_bwd_finalize_kernel<<<(n + 31) / 32, 32 * kSumSlices, 0, st>>>(1, d.ability_dim, 0, grid, part, table, g_table);
+  note_launch(2);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* mask,

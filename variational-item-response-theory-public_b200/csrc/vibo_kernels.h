@@ -24,6 +24,14 @@ cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8
                               const float* table, const float* amu, const float* S,
                               const float* g_mu, const float* g_lv, float* g_table, float* part,
                               cudaStream_t st);
+// Unconditional posterior: the forward also returns the per-person counts (n1, n_observed), the backward
+// works from them alone (no second pass over the rows).  cudaErrorNotSupported: use the pair above.
+cudaError_t launch_encode_counts(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                 const float* table, float* mu, float* lv, float* S, float* counts,
+                                 cudaStream_t st);
+cudaError_t launch_encode_bwd_counts(const vibo_desc& d, const float* counts, const float* table,
+                                     const float* amu, const float* S, const float* g_mu, const float* g_lv,
+                                     float* g_table, float* part, cudaStream_t st);
 cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* mask,
                         const float* ability, const float* item_feat, double* out_ll,
                         float* g_ability, float* g_item, double* part_ll, float* part_g,
@@ -41,6 +49,8 @@ cudaError_t stream_encode(const vibo_desc& d, const float* resp, const uint8_t* 
                           float* mu, float* lv, float* S, int* grid_out, cudaStream_t st);
 cudaError_t stream_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, float* counts,
                           cudaStream_t st);
+cudaError_t stream_encode_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table,
+                                 float* mu, float* lv, float* S, float* counts, cudaStream_t st);
 cudaError_t launch_person_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, float* counts,
                                  cudaStream_t st);
 cudaError_t stream_link(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* ability,

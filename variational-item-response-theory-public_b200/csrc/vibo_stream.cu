@@ -137,7 +137,7 @@ cudaError_t set_smem(K kernel, size_t smem) {
 
 template <int D, int M>
 cudaError_t run_encode(const vibo_desc& d, const StreamPlan& pl, const StreamParams& p, const float* table,
-                       float* mu, float* lv, float* S, cudaStream_t st) {
+                       float* mu, float* lv, float* S, float* counts, cudaStream_t st) {
   constexpr int NR = (2 * D <= 8) ? 8 : 4;
   cudaError_t e;
   if (d.conditional) {
@@ -147,7 +147,7 @@ cudaError_t run_encode(const vibo_desc& d, const StreamPlan& pl, const StreamPar
   } else {
     auto k = encode_stream_kernel<D, M, 8, false>;
     if ((e = set_smem(k, pl.smem)) != cudaSuccess) return e;
-    k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, d.missing_policy, table, mu, lv, S, nullptr);
+    k<<<pl.grid, pl.NW * 32, pl.smem, st>>>(p, d.missing_policy, table, mu, lv, S, counts);
   }
   return cudaGetLastError();
 }
@@ -317,8 +317,22 @@ cudaError_t stream_encode(const vibo_desc& d, const float* resp, const uint8_t* 
   const StreamParams p = make_params(d, pl, resp, mask, 0, nullptr);
   cudaError_t e = cudaSuccess;
   VIBO_STREAM_SWITCH_D(d.ability_dim,
-                       VIBO_STREAM_SWITCH_M(pl.M, e = (run_encode<kD, kM>(d, pl, p, table, mu, lv, S, st))));
+                       VIBO_STREAM_SWITCH_M(pl.M, e = (run_encode<kD, kM>(d, pl, p, table, mu, lv, S, nullptr, st))));
   if (grid_out) *grid_out = pl.grid;
+  return e;
+}
+
+// Unconditional posterior AND the per-person counts (n1, n_observed) it was formed from, in one pass:
+// the backward then needs no second pass over the rows (encode_bwd_counts_kernel, vibo_general.cu).
+cudaError_t stream_encode_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, const float* table,
+                                 float* mu, float* lv, float* S, float* counts, cudaStream_t st) {
+  if (d.conditional || counts == nullptr || !aligned16(resp) || !aligned16(mask)) return cudaErrorNotSupported;
+  const StreamPlan pl = stream_plan(d, 0, 0);
+  if (!pl.ok) return cudaErrorNotSupported;
+  const StreamParams p = make_params(d, pl, resp, mask, 0, nullptr);
+  cudaError_t e = cudaSuccess;
+  VIBO_STREAM_SWITCH_D(d.ability_dim,
+                       VIBO_STREAM_SWITCH_M(pl.M, e = (run_encode<kD, kM>(d, pl, p, table, mu, lv, S, counts, st))));
   return e;
 }
 

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(512) encode_stream_kernel(const __grid_constan
                                                             float* __restrict__ out_mu, float* __restrict__ out_lv,
                                                             float* __restrict__ out_S,
                                                             float* __restrict__ out_counts) {
-  // out_counts (unconditional only): write (n1, n_observed) per person instead of the posterior
+  // out_counts (unconditional only): also write (n1, n_observed) per person -- the sufficient statistics the
+  // backward pass needs (encode_bwd_counts_kernel) -- or, with out_mu == nullptr, only those
   extern __shared__ __align__(128) unsigned char smem[];
   const StreamCtx cx = stream_setup(p, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = blockDim.x >> 5;
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(512) encode_stream_kernel(const __grid_constan
             out_counts[(c * R + r) * 2] = n1;
             out_counts[(c * R + r) * 2 + 1] = (float)I - nm;
           }
-          continue;
+          if (out_mu == nullptr) continue;   // counts only (vibo_person_counts)
         }
         const float nz = (float)I - nm - n1;
         const float mu0 = table[d], mu1 = table[2 * D + d];

@@ -144,15 +144,30 @@ class EncodePosterior(torch.autograd.Function):
     @staticmethod
     def forward(ctx, response, mask, table, conditional, missing_policy):
         tbl = table.detach().contiguous()
-        mu, lv, S = K.encode(response, mask, tbl, conditional=conditional, missing_policy=missing_policy)
-        ctx.save_for_backward(response, mask, tbl, mu, S)
-        ctx.cfg = (conditional, missing_policy)
+        counts = None
+        if not conditional and table.requires_grad:
+            # unconditional table: the forward pass also leaves the per-person counts, and the backward works
+            # from them alone (one pass over the rows instead of two)
+            out = K.encode_counts(response, mask, tbl, missing_policy=missing_policy)
+            if out is not None:
+                mu, lv, S, counts = out
+        if counts is None:
+            mu, lv, S = K.encode(response, mask, tbl, conditional=conditional, missing_policy=missing_policy)
+            ctx.save_for_backward(response, mask, tbl, mu, S)
+        else:
+            ctx.save_for_backward(counts, tbl, mu, S)
+        ctx.cfg = (conditional, missing_policy, counts is not None, response.shape[1])
         return mu, lv
 
     @staticmethod
     def backward(ctx, g_mu, g_lv):
+        conditional, missing_policy, by_counts, num_item = ctx.cfg
+        if by_counts:
+            counts, tbl, mu, S = ctx.saved_tensors
+            g_table = K.encode_backward_counts(counts, tbl, mu, S, g_mu.contiguous(), g_lv.contiguous(),
+                                               num_item=num_item, missing_policy=missing_policy)
+            return None, None, g_table, None, None
         response, mask, tbl, mu, S = ctx.saved_tensors
-        conditional, missing_policy = ctx.cfg
         g_table = K.encode_backward(response, mask, tbl, mu, S, g_mu.contiguous(), g_lv.contiguous(),
                                     conditional=conditional, missing_policy=missing_policy)
         return None, None, g_table, None, None

@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import Desc, ELBO_KL, ELBO_SAMPLE, MISSING_DROP, MISSING_PRIOR  # noqa: F401
 
 _workspaces = {}
+ERR_UNSUPPORTED = -2   # VIBO_ERR_UNSUPPORTED (include/vibo_b200.h)
 
 
 def item_feat_width(irt_model: int, ability_dim: int) -> int:
@@ -157,6 +158,42 @@ def encode(response, mask, table, *, conditional, missing_policy=MISSING_PRIOR):
                                  _ptr(mu), _ptr(lv), _ptr(S), _stream(response.device))
     _lib.check(rc, "vibo_encode")
     return mu, lv, S
+
+
+def encode_counts(response, mask, table, *, missing_policy=MISSING_PRIOR):
+    """vibo_encode_counts (unconditional posterior) -> (ability_mu, ability_logvar, precision_sum, counts) with
+    counts (P, 2) = (observed ones, observed cells), or None when the rows are not covered (unaligned views):
+    the caller then uses encode / encode_backward."""
+    _check_rows(response, mask)
+    P, I = response.shape
+    D = table.shape[-1] // 2
+    desc = make_desc(P, I, D, 1, False, missing_policy)
+    mu = torch.empty(P, D, dtype=torch.float32, device=response.device)
+    lv = torch.empty_like(mu)
+    S = torch.empty_like(mu)
+    counts = torch.empty(P, 2, dtype=torch.float32, device=response.device)
+    rc = _lib.load().vibo_encode_counts(C.byref(desc), _ptr(response), _ptr(mask), _ptr(table.contiguous()),
+                                        _ptr(mu), _ptr(lv), _ptr(S), _ptr(counts), _stream(response.device))
+    if rc == ERR_UNSUPPORTED:
+        return None
+    _lib.check(rc, "vibo_encode_counts")
+    return mu, lv, S, counts
+
+
+def encode_backward_counts(counts, table, ability_mu, precision_sum, g_mu, g_logvar, *, num_item,
+                           missing_policy=MISSING_PRIOR):
+    """vibo_encode_backward_counts -> g_table (2, 1, 2D), from the counts of encode_counts (no pass over the
+    rows)."""
+    P, D = ability_mu.shape
+    desc = make_desc(P, num_item, D, 1, False, missing_policy)
+    g_table = torch.empty_like(table)
+    ws = workspace(desc, ability_mu.device)
+    rc = _lib.load().vibo_encode_backward_counts(
+        C.byref(desc), _ptr(counts), _ptr(table), _ptr(ability_mu), _ptr(precision_sum),
+        _ptr(g_mu.contiguous()), _ptr(g_logvar.contiguous()), _ptr(g_table), _ptr(ws), ws.numel(),
+        _stream(ability_mu.device))
+    _lib.check(rc, "vibo_encode_backward_counts")
+    return g_table
 
 
 def encode_backward(response, mask, table, ability_mu, precision_sum, g_mu, g_logvar, *,
