@@ -379,6 +379,21 @@ int vibo_flow_person_backward(const vibo_desc* desc, int n_flows, const float* a
                               size_t workspace_bytes, void* stream);
 
 /*
+ * Planar-flow parameter chain.  The reference keeps each flow's u (D), w (D), b (1) as separate
+ * parameters (flows.py:14-17, state_dict keys flows.{k}.{u,w,b}) and corrects u for invertibility inside
+ * PlanarFlow.forward (flows.py:26-29):  uhat = u + (softplus(w.u) - 1 - w.u) w / |w|^2.
+ * vibo_planar_params_forward gathers the K flows' parameters (u, w, b: HOST arrays of K DEVICE pointers) into
+ * the stacked (uhat, w_out (K, D), b_out (K)) the per-row flow kernels take; the backward maps
+ * d loss / d (uhat, w_out, b_out) to d loss / d (u, w, b) as stacked (K, D), (K, D), (K) rows.
+ * One launch each way instead of ~13 / ~25 elementwise launches of the autograd formulation.
+ */
+int vibo_planar_params_forward(int n_flows, int dim, const float* const* u, const float* const* w,
+                               const float* const* b, float* uhat, float* w_out, float* b_out, void* stream);
+int vibo_planar_params_backward(int n_flows, int dim, const float* const* u, const float* const* w,
+                                const float* g_uhat, const float* g_w_out, const float* g_b_out, float* g_u,
+                                float* g_w, float* g_b, void* stream);
+
+/*
  * Per-step exchange of the person-sharded run (one process per GPU, one node): in-place SUM over
  * the ranks of a small float buffer ([loss | parameter gradients], the `optimizer.step()` input of
  * vibo.py:266-268 when persons are split over GPUs).  One kernel over NVLink peer memory (CUDA

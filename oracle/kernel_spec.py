@@ -229,6 +229,25 @@ def encode_backward(response, mask, table, ability_dim, S, ability_mu, g_mu, g_l
     return g_table
 
 
+def planar_params(u, w, g_uhat=None, g_w_out=None):
+    """Spec of vibo_planar_params_forward / _backward (reference flows.py:26-29): u, w (K, D) ->
+    uhat = u + c w, c = (softplus(a) - 1 - a) / n, a = w.u, n = |w|^2 (torch softplus: threshold 20);
+    with (g_uhat, g_w_out) also the gradients of u and w (b passes through unchanged)."""
+    a = (u * w).sum(1, keepdims=True)
+    n = (w * w).sum(1, keepdims=True)
+    sp = np.where(a > 20.0, a, np.log1p(np.exp(np.minimum(a, 20.0))))
+    c = (sp - 1.0 - a) / n
+    uhat = u + c * w
+    if g_uhat is None:
+        return uhat
+    sig = np.where(a > 20.0, 1.0, 1.0 / (1.0 + np.exp(-a)))
+    gw = (g_uhat * w).sum(1, keepdims=True)
+    dc_da, dc_dn = (sig - 1.0) / n, -c / n
+    g_u = g_uhat + gw * dc_da * w
+    g_w = g_w_out + c * g_uhat + gw * (dc_da * u + 2.0 * dc_dn * w)
+    return uhat, g_u, g_w
+
+
 def encode_backward_counts(counts, table, ability_dim, S, ability_mu, g_mu, g_logvar):
     """encode_backward for the UNCONDITIONAL table (one expert per response value, It = 1) from the
     per-person counts (observed ones, observed cells) of person_counts: the row enters A^r, B^r only as

@@ -617,3 +617,32 @@ def test_count_based_unconditional_encode_backward(vb, P, I, D, missing, policy)
         big_r = torch.zeros(P * I + 1, device=dev)
         big_r[1:] = r.reshape(-1)
         assert vb.kernels.encode_counts(big_r[1:].view(P, I), m, t, missing_policy=policy) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,D", [(1, 1), (2, 1), (2, 2), (3, 5), (8, 8)])
+def test_planar_params_kernels(vb, K, D):
+    """vibo_planar_params_forward / _backward (the flows' separate u, w, b -> stacked uhat, w, b and back) against
+    the fp64 oracle spec, and NormalizingFlows.stacked_parameters through them against float64 autograd of the
+    reference formulation."""
+    from vibo_b200.flows import NormalizingFlows
+    torch.manual_seed(K * 7 + D)
+    nf = NormalizingFlows(D, n_flows=K).to("cuda")
+    if K > 1:
+        with torch.no_grad():
+            nf.flows[0].u.fill_(6.0)
+            nf.flows[0].w.fill_(4.0)   # w.u > 20: past the softplus threshold
+    uhat, w, b = nf.stacked_parameters()
+    g_uhat, g_w, g_b = torch.randn_like(uhat), torch.randn_like(w), torch.randn_like(b)
+    ((uhat * g_uhat).sum() + (w * g_w).sum() + (b * g_b).sum()).backward()
+    torch.cuda.synchronize()
+    u64 = np.stack([f.u.detach().cpu().numpy() for f in nf.flows]).astype(np.float64)
+    w64 = np.stack([f.w.detach().cpu().numpy() for f in nf.flows]).astype(np.float64)
+    ref_uhat, ref_gu, ref_gw = KS.planar_params(u64, w64, g_uhat.cpu().numpy().astype(np.float64),
+                                                g_w.cpu().numpy().astype(np.float64))
+    assert np.allclose(uhat.detach().cpu().numpy(), ref_uhat, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(w.detach().cpu().numpy(), w64.astype(np.float32))
+    for k, f in enumerate(nf.flows):
+        assert np.allclose(f.u.grad.cpu().numpy(), ref_gu[k], rtol=1e-4, atol=1e-5), k
+        assert np.allclose(f.w.grad.cpu().numpy(), ref_gw[k], rtol=1e-4, atol=1e-5), k
+        assert np.allclose(f.b.grad.cpu().numpy(), g_b[k:k + 1].cpu().numpy()), k

@@ -203,3 +203,25 @@ def test_count_based_unconditional_encode_backward_spec(D, policy, missing):
     n0, n1, _ = KS.person_counts(resp, mask)
     got = KS.encode_backward_counts(np.stack([n1, n0 + n1], 1), table, D, enc["S"], enc["ability_mu"], g_mu, g_lv)
     assert np.allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("K,D", [(1, 1), (2, 1), (2, 2), (8, 7)])
+def test_planar_params_spec_matches_reference_flow_correction(K, D):
+    """oracle.kernel_spec.planar_params (spec of vibo_planar_params_forward / _backward) against float64 autograd
+    of the reference's invertibility correction (flows.py:26-29), including a flow past the softplus threshold."""
+    g = torch.Generator().manual_seed(K * 10 + D)
+    u = torch.randn(K, D, generator=g, dtype=torch.float64)
+    w = torch.randn(K, D, generator=g, dtype=torch.float64)
+    if K > 1:
+        u[0], w[0] = 6.0, 4.0   # w.u = 24 D > 20: softplus is the identity there
+    u.requires_grad_(True)
+    w.requires_grad_(True)
+    uw = (u * w).sum(1, keepdim=True)
+    uhat = u + (torch.nn.functional.softplus(uw) - 1.0 - uw) * w / (w * w).sum(1, keepdim=True)
+    g_uhat = torch.randn(K, D, generator=g, dtype=torch.float64)
+    g_wout = torch.randn(K, D, generator=g, dtype=torch.float64)
+    (uhat * g_uhat).sum().add((w * g_wout).sum()).backward()
+    got_uhat, got_gu, got_gw = KS.planar_params(u.detach().numpy(), w.detach().numpy(), g_uhat.numpy(), g_wout.numpy())
+    assert np.allclose(got_uhat, uhat.detach().numpy(), rtol=1e-12, atol=1e-12)
+    assert np.allclose(got_gu, u.grad.numpy(), rtol=1e-10, atol=1e-12)
+    assert np.allclose(got_gw, w.grad.numpy(), rtol=1e-10, atol=1e-12)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "vibo_pack": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_unpack": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_encode": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p]),
+    "vibo_planar_params_forward": (C.c_int, [C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p]),
+    "vibo_planar_params_backward": (C.c_int, [C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vibo_person_counts": (C.c_int, [_PD, _p, _p, _p, _p]),
     "vibo_encode_counts": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vibo_encode_backward_counts": (C.c_int, [_PD, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),

@@ -462,6 +462,34 @@ int vibo_flow_person_backward(const vibo_desc* desc, int n_flows, const float* a
   return VIBO_OK;
 }
 
+int vibo_planar_params_forward(int n_flows, int dim, const float* const* u, const float* const* w,
+                               const float* const* b, float* uhat, float* w_out, float* b_out, void* stream) {
+  if (n_flows < 1 || n_flows > 8 || dim < 1 || dim > VIBO_MAX_ABILITY_DIM)
+    return fail(VIBO_ERR_UNSUPPORTED, "n_flows must be in 1..8 and dim in 1..8");
+  if (!u || !w || !b || !uhat || !w_out || !b_out) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  for (int k = 0; k < n_flows; ++k)
+    if (!u[k] || !w[k] || !b[k]) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL parameter pointer");
+  VIBO_CUDA(vibo::launch_planar_params_forward(n_flows, dim, u, w, b, uhat, w_out, b_out,
+                                               static_cast<cudaStream_t>(stream)),
+            "planar_params_forward");
+  return VIBO_OK;
+}
+
+int vibo_planar_params_backward(int n_flows, int dim, const float* const* u, const float* const* w,
+                                const float* g_uhat, const float* g_w_out, const float* g_b_out, float* g_u,
+                                float* g_w, float* g_b, void* stream) {
+  if (n_flows < 1 || n_flows > 8 || dim < 1 || dim > VIBO_MAX_ABILITY_DIM)
+    return fail(VIBO_ERR_UNSUPPORTED, "n_flows must be in 1..8 and dim in 1..8");
+  if (!u || !w || !g_uhat || !g_w_out || !g_b_out || !g_u || !g_w || !g_b)
+    return fail(VIBO_ERR_BAD_ARGUMENT, "NULL pointer");
+  for (int k = 0; k < n_flows; ++k)
+    if (!u[k] || !w[k]) return fail(VIBO_ERR_BAD_ARGUMENT, "NULL parameter pointer");
+  VIBO_CUDA(vibo::launch_planar_params_backward(n_flows, dim, u, w, g_uhat, g_w_out, g_b_out, g_u, g_w, g_b,
+                                                static_cast<cudaStream_t>(stream)),
+            "planar_params_backward");
+  return VIBO_OK;
+}
+
 int vibo_param_forward(const vibo_desc* desc, int hidden_dim, const float* mu_lookup,
                        const float* logvar_lookup, const float* eps_item, const float* w0,
                        const float* b0, const float* w2, const float* b2, const float* w4,

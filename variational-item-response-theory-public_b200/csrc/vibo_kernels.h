@@ -79,6 +79,12 @@ cudaError_t launch_flow_person_forward(int64_t P, int D, int K, const float* amu
                                        const float* eps, const float* uhat, const float* w, const float* b,
                                        float* ability0, float* ability_k, double* part_term, double* out_term,
                                        cudaStream_t st);
+cudaError_t launch_planar_params_forward(int K, int D, const float* const* u, const float* const* w,
+                                         const float* const* b, float* uhat, float* w_out, float* b_out,
+                                         cudaStream_t st);
+cudaError_t launch_planar_params_backward(int K, int D, const float* const* u, const float* const* w,
+                                          const float* g_uhat, const float* g_w_out, const float* g_b_out,
+                                          float* g_u, float* g_w, float* g_b, cudaStream_t st);
 cudaError_t launch_flow_person_backward(int64_t P, int D, int K, const float* amu, const float* alv,
                                         const float* eps, const float* uhat, const float* w, const float* b,
                                         const float* g_ability_k, const float* g_term, float* g_mu, float* g_lv,

@@ -194,6 +194,38 @@ class LinkLogLik(torch.autograd.Function):
         return None, None, g * g_ab, g * g_it, None
 
 
+class PlanarParams(torch.autograd.Function):
+    """The K planar flows' separate parameters (u_k, w_k, b_k) -> stacked (uhat (K, D), w (K, D), b (K)) with the
+    invertibility correction of reference flows.py:26-29, one kernel each way
+    (vibo_planar_params_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, n_flows, *params):
+        us, ws, bs = params[:n_flows], params[n_flows:2 * n_flows], params[2 * n_flows:]
+        us = [t.detach() for t in us]
+        ws = [t.detach() for t in ws]
+        uhat, w_out, b_out = K.planar_params_forward(us, ws, [t.detach() for t in bs])
+        ctx.save_for_backward(*us, *ws)
+        ctx.n_flows = n_flows
+        return uhat, w_out, b_out
+
+    @staticmethod
+    def backward(ctx, g_uhat, g_w, g_b):
+        n = ctx.n_flows
+        saved = ctx.saved_tensors
+        us, ws = saved[:n], saved[n:]
+        D = us[0].numel()
+        dev = us[0].device
+        if g_uhat is None:
+            g_uhat = torch.zeros(n, D, device=dev)
+        if g_w is None:
+            g_w = torch.zeros(n, D, device=dev)
+        if g_b is None:
+            g_b = torch.zeros(n, device=dev)
+        gu, gw, gb = K.planar_params_backward(us, ws, g_uhat, g_w, g_b)
+        return (None, *[gu[k] for k in range(n)], *[gw[k] for k in range(n)], *[gb[k:k + 1] for k in range(n)])
+
+
 class FlowPerson(torch.autograd.Function):
     """Reparameterised ability draw + K planar flows + the person-side terms of the
     flow-form ELBO, one kernel each way (vibo_flow_person_forward / _backward).

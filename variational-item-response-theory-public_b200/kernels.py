@@ -196,6 +196,43 @@ def encode_backward_counts(counts, table, ability_mu, precision_sum, g_mu, g_log
     return g_table
 
 
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def planar_params_forward(us, ws, bs):
+    """vibo_planar_params_forward: the K flows' separate (u (D), w (D), b (1)) parameters -> stacked
+    (uhat (K, D), w (K, D), b (K)) with the invertibility correction of flows.py:26-29."""
+    Kf, D = len(us), us[0].numel()
+    dev = us[0].device
+    for t in list(us) + list(ws) + list(bs):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    uhat = torch.empty(Kf, D, dtype=torch.float32, device=dev)
+    w_out = torch.empty_like(uhat)
+    b_out = torch.empty(Kf, dtype=torch.float32, device=dev)
+    pu, pw, pb = _ptr_array(us), _ptr_array(ws), _ptr_array(bs)
+    rc = _lib.load().vibo_planar_params_forward(Kf, D, pu, pw, pb, _ptr(uhat), _ptr(w_out), _ptr(b_out),
+                                                _stream(dev))
+    _lib.check(rc, "vibo_planar_params_forward")
+    return uhat, w_out, b_out
+
+
+def planar_params_backward(us, ws, g_uhat, g_w_out, g_b_out):
+    """vibo_planar_params_backward -> (g_u (K, D), g_w (K, D), g_b (K)) for the separate parameters."""
+    Kf, D = len(us), us[0].numel()
+    dev = us[0].device
+    g_u = torch.empty(Kf, D, dtype=torch.float32, device=dev)
+    g_w = torch.empty_like(g_u)
+    g_b = torch.empty(Kf, dtype=torch.float32, device=dev)
+    pu, pw = _ptr_array(us), _ptr_array(ws)
+    rc = _lib.load().vibo_planar_params_backward(Kf, D, pu, pw, _ptr(g_uhat.contiguous()),
+                                                 _ptr(g_w_out.contiguous()), _ptr(g_b_out.contiguous()),
+                                                 _ptr(g_u), _ptr(g_w), _ptr(g_b), _stream(dev))
+    _lib.check(rc, "vibo_planar_params_backward")
+    return g_u, g_w, g_b
+
+
 def encode_backward(response, mask, table, ability_mu, precision_sum, g_mu, g_logvar, *,
                     conditional, missing_policy=MISSING_PRIOR):
     """vibo_encode_backward -> g_table (2, It, 2D)."""
