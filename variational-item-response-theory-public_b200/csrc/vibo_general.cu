@@ -671,7 +671,7 @@ cudaError_t launch_encode_bwd_counts(const vibo_desc& d, const float* counts, co
                                      float* g_table, float* part, cudaStream_t st) {
   if (d.conditional) return cudaErrorNotSupported;
   int64_t blocks = (d.num_person + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 4;
+  const int64_t cap = (int64_t)sm_count();   // few partials: the finalize walks them in a dependent chain
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const int grid = (int)blocks;

@@ -267,7 +267,12 @@ class ShardedElboTrainer:
     def _train_pre(self, response, mask, seed, eps_item=None, eps_ability=None):
         self.flat.zero_()
         loss = self._loss(response, mask, seed, eps_item, eps_ability)
-        loss.backward()
+        # gradients straight into the flat buffer with ONE multi-tensor copy: loss.backward() would add each
+        # parameter's gradient into its (zeroed) view with a launch of its own
+        grads = torch.autograd.grad(loss, self.params, allow_unused=True)
+        dst = [p.grad for p, g in zip(self.params, grads) if g is not None]
+        if dst:
+            torch._foreach_copy_(dst, [g for g in grads if g is not None])
         self.flat[0:1].copy_(loss.detach().reshape(1))
 
     def _train_post(self):
