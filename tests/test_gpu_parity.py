@@ -612,11 +612,33 @@ def test_count_based_unconditional_encode_backward(vb, P, I, D, missing, policy)
                              enc["ability_mu"], g_mu.astype(np.float64), g_lv.astype(np.float64))
     assert rel_l2(got.cpu().numpy(), ref) < TOL, rel_l2(got.cpu().numpy(), ref)
     assert rel_l2(got.cpu().numpy(), old.cpu().numpy()) < TOL
-    # rows that are not 16-byte aligned are not covered: the wrapper returns None and the caller uses the row-level pair
+    # narrow rows (I <= 256) are served by the warp-per-row kernel, which has no alignment requirement; for wider
+    # rows an unaligned view is not covered: the wrapper returns None and the caller uses the row-level pair
     if I % 4 != 0 and P > 1:
         big_r = torch.zeros(P * I + 1, device=dev)
         big_r[1:] = r.reshape(-1)
-        assert vb.kernels.encode_counts(big_r[1:].view(P, I), m, t, missing_policy=policy) is None
+        out_u = vb.kernels.encode_counts(big_r[1:].view(P, I), m, t, missing_policy=policy)
+        if I <= 256:
+            assert out_u is not None and torch.equal(out_u[0], mu) and torch.equal(out_u[3], counts)
+        else:
+            assert out_u is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,I,D,missing,policy", [(5000, 95, 1, 0.1, 0), (777, 256, 3, 0.2, 1), (130, 33, 2, 0.0, 0)])
+def test_narrow_row_encode_matches_slab_stream(vb, monkeypatch, P, I, D, missing, policy):
+    """The warp-per-row unconditional encode (I <= 256) against the slab-stream kernel it replaces there
+    (VIBO_DISABLE_ROWWARP=1): identical counts, posterior equal to rounding."""
+    resp, mask, table, _, _ = _synth(P, I, D, 2, False, missing, seed=P + I)
+    dev = "cuda"
+    r, m, t = (torch.from_numpy(a).to(dev) for a in (resp, mask, table))
+    new = vb.kernels.encode_counts(r, m, t, missing_policy=policy)
+    monkeypatch.setenv("VIBO_DISABLE_ROWWARP", "1")
+    old = vb.kernels.encode_counts(r, m, t, missing_policy=policy)
+    torch.cuda.synchronize()
+    assert torch.equal(new[3], old[3])
+    for a, b in zip(new[:3], old[:3]):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
 
 
 @pytest.mark.gpu

@@ -237,6 +237,80 @@ __global__ void __launch_bounds__(32 * kSumSlices) encode_bwd_finalize_kernel(in
   }
 }
 
+// Unconditional encode for NARROW rows (I <= 256), one warp per row with direct coalesced loads.  The
+// unconditional posterior needs a row only through (observed ones, missing cells); for rows of a few hundred
+// bytes the slab-stream kernel's per-chunk chain (bulk copy -> wait -> reduce -> barrier) caps it near
+// 2.3 TB/s, while plain loads with four rows in flight per warp and 64 warps per SM are bound by DRAM latency
+// alone.  Same posterior arithmetic as encode_stream_kernel<.., COND = false>; no alignment requirement.
+// out_counts (P, 2) = (observed ones, observed cells) and / or the posterior (out_mu == nullptr: counts only).
+template <int D>
+__global__ void __launch_bounds__(256) encode_rows_uncond_kernel(int64_t P, int I, int missing_policy,
+                                                                 const float* __restrict__ resp,
+                                                                 const uint8_t* __restrict__ mask,
+                                                                 const float* __restrict__ table,
+                                                                 float* __restrict__ out_mu,
+                                                                 float* __restrict__ out_lv,
+                                                                 float* __restrict__ out_S,
+                                                                 float* __restrict__ out_counts) {
+  constexpr int NRW = 4;   // rows per warp and trip
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float prior_tau = (missing_policy == VIBO_MISSING_PRIOR) ? 1.0f / (1.0f + kPoeEps) : 0.0f;
+  for (int64_t row0 = gwarp * NRW; row0 < P; row0 += nwarps * NRW) {
+    const float* xr[NRW];
+    const uint8_t* mr[NRW];
+#pragma unroll
+    for (int q = 0; q < NRW; ++q) {
+      const int64_t row = row0 + q < P ? row0 + q : P - 1;   // clamped: the result of a row past the end is dropped
+      xr[q] = resp + row * I;
+      mr[q] = mask + row * I;
+    }
+    uint32_t cnt[NRW];   // ones | missing << 16  (I <= 2048)
+#pragma unroll
+    for (int q = 0; q < NRW; ++q) cnt[q] = 0;
+#pragma unroll 2
+    for (int j = lane; j < I; j += 32) {
+      float x[NRW];
+      uint8_t o[NRW];
+#pragma unroll
+      for (int q = 0; q < NRW; ++q) {
+        x[q] = xr[q][j];
+        o[q] = mr[q][j];
+      }
+#pragma unroll
+      for (int q = 0; q < NRW; ++q) cnt[q] += o[q] != 0 ? (x[q] > 0.5f ? 1u : 0u) : 65536u;
+    }
+#pragma unroll
+    for (int q = 0; q < NRW; ++q) cnt[q] = __reduce_add_sync(0xffffffffu, cnt[q]);
+    // lane q finishes row row0 + q
+    uint32_t c = cnt[0];
+#pragma unroll
+    for (int q = 1; q < NRW; ++q) c = lane == q ? cnt[q] : c;
+    const int64_t row = row0 + lane;
+    if (lane < NRW && row < P) {
+      const float n1 = (float)(c & 0xffffu), nm = (float)(c >> 16);
+      if (out_counts != nullptr) {
+        out_counts[row * 2] = n1;
+        out_counts[row * 2 + 1] = (float)I - nm;
+      }
+      if (out_mu != nullptr) {
+        const float nz = (float)I - nm - n1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float mu0 = table[d], mu1 = table[2 * D + d];
+          const float ta0 = 1.0f / (expf(table[D + d]) + kPoeEps), ta1 = 1.0f / (expf(table[3 * D + d]) + kPoeEps);
+          const float sv = fmaf(nz, ta0, fmaf(n1, ta1, nm * prior_tau));
+          const float nv = fmaf(nz, mu0 * ta0, n1 * (mu1 * ta1));
+          out_mu[row * D + d] = nv / sv;
+          out_lv[row * D + d] = logf(1.0f / sv);
+          if (out_S) out_S[row * D + d] = sv;
+        }
+      }
+    }
+  }
+}
+
 // Unconditional encode backward from the forward pass's per-person counts.  The unconditional table has ONE
 // entry per response value, so A^r = sum_i n^r_i GN_i and B^r = sum_i n^r_i GS_i (n^1 = observed ones,
 // n^0 = observed - ones; missing cells carry no table entry under either policy) need 16 + 16 D bytes per
@@ -623,7 +697,11 @@ static cudaError_t launch_link_dm(const vibo_desc& d, const float* resp, const u
 
 cudaError_t launch_encode(const vibo_desc& d, const float* resp, const uint8_t* mask,
                           const float* table, float* mu, float* lv, float* S, cudaStream_t st) {
-  cudaError_t e = stream_encode(d, resp, mask, table, mu, lv, S, nullptr, st);
+  cudaError_t e = launch_encode_rows_uncond(d, resp, mask, table, mu, lv, S, nullptr, st);
+  if (e == cudaErrorNotSupported) {
+    (void)cudaGetLastError();
+    e = stream_encode(d, resp, mask, table, mu, lv, S, nullptr, st);
+  }
   if (e != cudaErrorNotSupported) {
     if (e == cudaSuccess) note_launch();
     return e;
@@ -656,12 +734,38 @@ cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8
   return e;
 }
 
+// cudaErrorNotSupported unless the posterior is unconditional and the rows are narrow.
+cudaError_t launch_encode_rows_uncond(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                      const float* table, float* mu, float* lv, float* S, float* counts,
+                                      cudaStream_t st) {
+  const char* off = getenv("VIBO_DISABLE_ROWWARP");
+  if (off != nullptr && off[0] == '1') return cudaErrorNotSupported;
+  const char* off2 = getenv("VIBO_DISABLE_STREAM");   // the path-coverage tests' switch to the legacy kernels
+  if (off2 != nullptr && off2[0] == '1') return cudaErrorNotSupported;
+  if (d.conditional || d.num_item > 256 || d.num_person < 1) return cudaErrorNotSupported;
+  if (mu == nullptr && counts == nullptr) return cudaErrorNotSupported;
+  int64_t blocks = (d.num_person + 31) / 32;   // 8 warps x 4 rows per block and trip
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cudaError_t e = cudaSuccess;
+  VIBO_SWITCH_D(mu != nullptr ? d.ability_dim : 1,
+                (encode_rows_uncond_kernel<kD><<<(int)blocks, 256, 0, st>>>(d.num_person, d.num_item, d.missing_policy,
+                                                                         resp, mask, table, mu, lv, S, counts)));
+  (void)e;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_encode_counts(const vibo_desc& d, const float* resp, const uint8_t* mask,
                                  const float* table, float* mu, float* lv, float* S, float* counts,
                                  cudaStream_t st) {
   const char* off = getenv("VIBO_DISABLE_COUNTS_BWD");
   if (off != nullptr && off[0] == '1') return cudaErrorNotSupported;
-  const cudaError_t e = stream_encode_counts(d, resp, mask, table, mu, lv, S, counts, st);
+  cudaError_t e = launch_encode_rows_uncond(d, resp, mask, table, mu, lv, S, counts, st);
+  if (e == cudaErrorNotSupported) {
+    (void)cudaGetLastError();
+    e = stream_encode_counts(d, resp, mask, table, mu, lv, S, counts, st);
+  }
   if (e == cudaSuccess) note_launch();
   return e;
 }
@@ -727,7 +831,11 @@ cudaError_t launch_link(const vibo_desc& d, const float* resp, const uint8_t* ma
 
 cudaError_t launch_person_counts(const vibo_desc& d, const float* resp, const uint8_t* mask, float* counts,
                                  cudaStream_t st) {
-  cudaError_t e = stream_counts(d, resp, mask, counts, st);
+  cudaError_t e = launch_encode_rows_uncond(d, resp, mask, nullptr, nullptr, nullptr, nullptr, counts, st);
+  if (e == cudaErrorNotSupported) {
+    (void)cudaGetLastError();
+    e = stream_counts(d, resp, mask, counts, st);
+  }
   if (e != cudaErrorNotSupported) {
     if (e == cudaSuccess) note_launch();
     return e;

@@ -26,6 +26,10 @@ cudaError_t launch_encode_bwd(const vibo_desc& d, const float* resp, const uint8
                               cudaStream_t st);
 // Unconditional posterior: the forward also returns the per-person counts (n1, n_observed), the backward
 // works from them alone (no second pass over the rows).  cudaErrorNotSupported: use the pair above.
+// narrow rows (I <= 256), unconditional: one warp per row with direct loads; mu / counts may each be NULL
+cudaError_t launch_encode_rows_uncond(const vibo_desc& d, const float* resp, const uint8_t* mask,
+                                      const float* table, float* mu, float* lv, float* S, float* counts,
+                                      cudaStream_t st);
 cudaError_t launch_encode_counts(const vibo_desc& d, const float* resp, const uint8_t* mask,
                                  const float* table, float* mu, float* lv, float* S, float* counts,
                                  cudaStream_t st);
