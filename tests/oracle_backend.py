@@ -110,6 +110,20 @@ def encode_backward_counts(counts, table, ability_mu, precision_sum, g_mu, g_log
     return _t(g, table)
 
 
+def planar_params_forward(us, ws, bs):
+    u, w = np.stack([_np(t) for t in us]), np.stack([_np(t) for t in ws])
+    uhat = KS.planar_params(u, w)
+    like = us[0]
+    return _t(uhat, like), _t(w, like), _t(np.concatenate([_np(t) for t in bs]), like)
+
+
+def planar_params_backward(us, ws, g_uhat, g_w_out, g_b_out):
+    u, w = np.stack([_np(t) for t in us]), np.stack([_np(t) for t in ws])
+    _, g_u, g_w = KS.planar_params(u, w, _np(g_uhat), _np(g_w_out))
+    like = us[0]
+    return _t(g_u, like), _t(g_w, like), g_b_out.clone()
+
+
 def link_loglik(response, mask, ability, item_feat, *, irt_model, want_grads=True):
     r = KS.link_loglik(_np(response), _np(mask, np.uint8), _np(ability), _np(item_feat), irt_model,
                        want_grads)
@@ -138,6 +152,6 @@ def install(monkeypatch):
     import vibo_b200
     K = vibo_b200.kernels
     for name in ("fused_elbo", "encode", "encode_backward", "encode_counts", "encode_backward_counts",
-                 "link_loglik", "decode",
+                 "planar_params_forward", "planar_params_backward", "link_loglik", "decode",
                  "bernoulli_loglik", "_check_rows", "philox_normal"):
         monkeypatch.setattr(K, name, globals()[name])

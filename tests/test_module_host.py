@@ -191,3 +191,30 @@ def test_vi_module_matches_reference():
         assert abs(loss.item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
         for k, p in model.named_parameters():
             assert rel_l2(p.grad.numpy(), z["grad/" + k]) < 1e-4, (fused, k)
+
+
+@pytest.mark.parametrize("K,D", [(1, 1), (2, 2), (3, 5)])
+def test_planar_params_function_host_logic(monkeypatch, K, D):
+    """functional.PlanarParams (the K flows' separate u, w, b -> stacked uhat, w, b; one kernel each way on the
+    GPU) on the oracle backend: outputs and every parameter gradient equal PyTorch autograd of the reference
+    formulation (flows.py:26-29) -- argument order, the per-parameter gradient views and the b pass-through."""
+    import oracle_backend
+    import vibo_b200
+    from vibo_b200 import functional as VF
+    from vibo_b200.flows import NormalizingFlows
+    oracle_backend.install(monkeypatch)
+    torch.manual_seed(K + 10 * D)
+    nf = NormalizingFlows(D, n_flows=K)
+    ref_uhat, ref_w, ref_b = nf.stacked_parameters()          # CPU parameters: the autograd formulation
+    g = [torch.randn_like(ref_uhat), torch.randn_like(ref_w), torch.randn_like(ref_b)]
+    (ref_uhat * g[0]).sum().add((ref_w * g[1]).sum()).add((ref_b * g[2]).sum()).backward()
+    ref_grads = [[f.u.grad.clone(), f.w.grad.clone(), f.b.grad.clone()] for f in nf.flows]
+    nf.zero_grad()
+    uhat, w, b = VF.PlanarParams.apply(K, *[f.u for f in nf.flows], *[f.w for f in nf.flows], *[f.b for f in nf.flows])
+    assert torch.allclose(uhat, ref_uhat.detach(), atol=1e-6) and torch.equal(w, ref_w.detach())
+    assert torch.equal(b, ref_b.detach())
+    (uhat * g[0]).sum().add((w * g[1]).sum()).add((b * g[2]).sum()).backward()
+    for f, (gu, gw, gb) in zip(nf.flows, ref_grads):
+        assert torch.allclose(f.u.grad, gu, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(f.w.grad, gw, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(f.b.grad, gb)
